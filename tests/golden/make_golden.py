@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Runs only where /root/reference exists (the build container).  It imports the
+reference's hot-path modules as they are: two stub
+modules stand in for ``pytorch_lightning`` and ``hydra`` (absent in this
+image), the model cfg is the reference's own ``conf/model/ddpmgblur.yaml``,
+weights come from ``weightgen.py`` and are loaded with ``load_state_dict``.
+
+Everything recorded here is what the reference computed on CPU (torch fp32):
+  forward_*.npz   one ``EGNN_dynamics_QM9._forward`` with intermediates
+  sample_*.npz    a full ``DiffusionQM9.sample`` with the raw randn draws,
+                  the gamma values of every step and the z trajectory
+  gamma.npz       GammaNetwork / PredefinedNoiseSchedule values
+  nodes_dist.npz  DistributionNodes draws under torch.manual_seed
+
+Usage:  python tests/golden/make_golden.py   (rewrites the .npz files)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/endiffusion"
+sys.path.insert(0, HERE)
+from weightgen import fill_state_dict  # noqa: E402
+
+
+# ----------------------------------------------------------------------------
+# reference import with stubs
+# ----------------------------------------------------------------------------
+def _install_stubs():
+    pl = types.ModuleType("pytorch_lightning")
+
+    class LightningModule(nn.Module):
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        def log(self, *a, **k):
+            pass
+
+    pl.LightningModule = LightningModule
+    sys.modules["pytorch_lightning"] = pl
+    hydra = types.ModuleType("hydra")
+    hutils = types.ModuleType("hydra.utils")
+    hutils.instantiate = lambda *a, **k: None
+    hydra.utils = hutils
+    sys.modules["hydra"] = hydra
+    sys.modules["hydra.utils"] = hutils
+
+
+class AttrDict(dict):
+    """attr + item access, like the OmegaConf node the reference receives."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def to_attr(d):
+    if isinstance(d, dict):
+        return AttrDict({k: to_attr(v) for k, v in d.items()})
+    return d
+
+
+class FixedNodes(nn.Module):
+    def __init__(self, sizes):
+        super().__init__()
+        self.sizes = list(sizes)
+
+    def sample(self, k):
+        assert k == len(self.sizes)
+        return list(self.sizes)
+
+
+def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned"):
+    _install_stubs()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import contextlib
+    import io
+
+    from train_module.diffusion_qm9 import DiffusionQM9
+
+    cfg = to_attr(yaml.safe_load(open(os.path.join(REF, "conf/model/ddpmgblur.yaml")))["cfg"])
+    cfg.dynamics.n_layers = n_layers
+    cfg.timesteps = timesteps
+    cfg.noise_schedule = noise_schedule
+    if noise_schedule != "learned":
+        cfg.pre_noise = to_attr({"noise_schedule": noise_schedule, "timesteps": timesteps,
+                                 "precision": 1e-4})
+        cfg.loss_type = "l2"
+    cfg.analyze = os.path.join(REF, "conf/analyze/GEOM.yaml")
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = DiffusionQM9(cfg)
+    model.cwd = ""
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = {k: torch.from_numpy(v) for k, v in fill_state_dict(shapes, seed).items()}
+    if noise_schedule != "learned":
+        sd["gamma.gamma"] = model.state_dict()["gamma.gamma"]
+    model.load_state_dict(sd)
+    model.eval()
+    return model
+
+
+def masks_for(sizes, N):
+    B = len(sizes)
+    node_mask = torch.zeros(B, N, 1)
+    edge_mask = torch.zeros(B, N, N)
+    for i, n in enumerate(sizes):
+        node_mask[i, :n] = 1
+        edge_mask[i, :n, :n] = 1 - torch.eye(n)
+    return node_mask.bool(), edge_mask.bool()
+
+
+# ----------------------------------------------------------------------------
+# cases
+# ----------------------------------------------------------------------------
+def case_forward(name, n_layers, sizes, N, seed):
+    model = make_reference(n_layers, 1000)
+    dyn = model.dynamics
+    B = len(sizes)
+    g = torch.Generator().manual_seed(seed)
+    node_mask, edge_mask = masks_for(sizes, N)
+    z = torch.randn(B, N, 11, generator=g) * node_mask
+    # CoG-free positions, as the sampler guarantees
+    nm = node_mask.float()
+    z[..., :3] -= (z[..., :3].sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
+    t = torch.rand(B, 1, generator=g)
+
+    rec = {}
+
+    def hook(tag):
+        def f(mod, inp, out):
+            if isinstance(out, tuple):
+                for i, o in enumerate(out):
+                    rec[f"{tag}.{i}"] = o.detach().clone().numpy()
+            else:
+                rec[tag] = out.detach().clone().numpy()
+        return f
+
+    hs = [dyn.egnn.embedding.register_forward_hook(hook("embedding")),
+          dyn.egnn.e_block_0.gcl_0.register_forward_hook(hook("b0.gcl0")),
+          dyn.egnn.e_block_0.gcl_1.register_forward_hook(hook("b0.gcl1")),
+          dyn.egnn.e_block_0.gcl_equiv.register_forward_hook(hook("b0.equiv")),
+          dyn.egnn.e_block_0.register_forward_hook(hook("b0")),
+          dyn.egnn.register_forward_hook(hook("egnn"))]
+    with torch.no_grad():
+        eps = dyn._forward(t, z, node_mask, edge_mask, None, None)
+    for h in hs:
+        h.remove()
+    out = dict(z=z.numpy(), t=t.numpy(), sizes=np.array(sizes, np.int32), eps=eps.numpy(),
+               n_layers=np.int32(n_layers), weight_seed=np.int32(2022),
+               h_embed=rec["embedding"], h_gcl0=rec["b0.gcl0.0"], h_gcl1=rec["b0.gcl1.0"],
+               x_equiv0=rec["b0.equiv"], h_block0=rec["b0.0"], x_block0=rec["b0.1"],
+               h_final=rec["egnn.0"], x_final=rec["egnn.1"])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "eps absmax", float(eps.abs().max()))
+
+
+def case_sample(name, n_layers, T, sizes, seed, noise_schedule="learned"):
+    model = make_reference(n_layers, T, noise_schedule=noise_schedule)
+    model.nodes_dist = FixedNodes(sizes)
+    B, N = len(sizes), max(sizes)
+
+    draws = []
+    real_randn = torch.randn
+
+    def rec_randn(*a, **k):
+        v = real_randn(*a, **k)
+        draws.append(v.clone().numpy())
+        return v
+
+    gam = []
+    h = model.gamma.register_forward_hook(
+        lambda m, i, o: gam.append((i[0].detach().clone().numpy(), o.detach().clone().numpy())))
+    zs = []
+    real_step = model.sample_p_zs_given_zt
+
+    def rec_step(*a, **k):
+        v = real_step(*a, **k)
+        zs.append(v.clone().numpy())
+        return v
+
+    model.sample_p_zs_given_zt = rec_step
+    torch.manual_seed(seed)
+    torch.randn = rec_randn
+    try:
+        res = model.sample(B, torch.device("cpu"))
+    finally:
+        torch.randn = real_randn
+    h.remove()
+    # draws: [x_T, h_T, (x_s, h_s) * T, x_final, h_final]
+    assert len(draws) == 2 * (T + 2), len(draws)
+    nx = np.stack(draws[0::2])          # [T+2, B, N, 3]
+    nh = np.stack(draws[1::2])          # [T+2, B, N, 8]
+    # gamma calls: per step (s, t), final (0)
+    assert len(gam) == 2 * T + 1
+    g_in = np.stack([g[0][:, 0] for g in gam])    # [2T+1, B]
+    g_out = np.stack([g[1][:, 0] for g in gam])
+    x = np.zeros((B, N, 3), np.float32)
+    hh = np.zeros((B, N, 8), np.float32)
+    for i, r in enumerate(res):
+        x[i, :sizes[i]] = r["x"].numpy()
+        hh[i, :sizes[i]] = r["h"].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), randn_x=nx, randn_h=nh,
+                        gamma_in=g_in, gamma_out=g_out, z_traj=np.stack(zs).astype(np.float32),
+                        x=x, h=hh, sizes=np.array(sizes, np.int32), T=np.int32(T),
+                        n_layers=np.int32(n_layers), weight_seed=np.int32(2022),
+                        sample_seed=np.int32(seed))
+    print(name, "x absmax", float(np.abs(x).max()), "h absmax", float(np.abs(hh).max()),
+          "z_traj absmax", float(np.abs(np.stack(zs)).max()))
+
+
+def case_gamma():
+    model = make_reference(1, 1000)
+    t = torch.linspace(0, 1, 41).view(-1, 1)
+    with torch.no_grad():
+        g4 = torch.stack([model.gamma(torch.full((4, 1), float(v))) for v in t[:, 0]])[:, 0, 0]
+        g_batched = model.gamma(t)[:, 0]
+    model2 = make_reference(1, 1000, noise_schedule="polynomial_2")
+    with torch.no_grad():
+        gp = model2.gamma(t)[:, 0]
+    np.savez_compressed(os.path.join(HERE, "gamma.npz"), t=t[:, 0].numpy(), gamma_b4=g4.numpy(),
+                        gamma_batched=g_batched.numpy(), gamma_poly2=gp.numpy(),
+                        gamma_poly2_table=model2.gamma.gamma.detach().numpy())
+    print("gamma", g4[:3].tolist(), gp[:3].tolist())
+
+
+def case_nodes_dist():
+    model = make_reference(1, 1000)
+    torch.manual_seed(0)
+    a = model.nodes_dist.sample(64)
+    b = model.nodes_dist.sample(7)
+    np.savez_compressed(os.path.join(HERE, "nodes_dist.npz"), seed0_64=np.array(a, np.int32),
+                        then_7=np.array(b, np.int32))
+    print("nodes_dist", a[:8])
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    case_forward("forward_l2", n_layers=2, sizes=[12, 7, 1, 2], N=12, seed=11)
+    case_forward("forward_l1_pad", n_layers=1, sizes=[5, 9, 3], N=16, seed=12)
+    case_sample("sample_c1", n_layers=6, T=50, sizes=[20, 20, 20, 20], seed=0)
+    case_sample("sample_ragged_l9", n_layers=9, T=20, sizes=[10, 6, 9], seed=1)
+    case_sample("sample_poly_l1", n_layers=1, T=10, sizes=[4, 8], seed=2, noise_schedule="polynomial_2")
+    case_gamma()
+    case_nodes_dist()
