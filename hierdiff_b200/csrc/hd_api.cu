@@ -1,0 +1,576 @@
+// hd_api.cu - the C ABI (include/hierdiff_b200.h): argument checking, orchestration of one
+// EGNN forward, and the small per-node / per-molecule kernels around the edge kernels
+// (embedding, output head, velocity + centre-of-gravity projection, diffusion update).
+#include <cmath>
+#include <cstring>
+
+#include "hd_common.cuh"
+
+namespace hd {
+const char* last_error();
+int64_t launch_count();
+int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// en_dynamics.py:56-74: xh*node_mask, split, append time.  One thread per (row, channel).
+// ---------------------------------------------------------------------------------------
+__global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t, const int32_t* __restrict__ sizes,
+                       int B, int N, int F, float* __restrict__ hin, float* __restrict__ x, float* __restrict__ x0,
+                       int32_t* __restrict__ nanflag) {
+  const int D = 3 + F, Fi = F + 1;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *nanflag = 0;
+  if (idx >= (int64_t)B * N * (D + 1)) return;
+  const int64_t r = idx / (D + 1);
+  const int ch = (int)(idx % (D + 1));
+  const int b = (int)(r / N), i = (int)(r % N);
+  const float mk = i < sizes[b] ? 1.f : 0.f;
+  if (ch < 3) {
+    const float v = z[r * D + ch] * mk;
+    x[r * 3 + ch] = v;
+    x0[r * 3 + ch] = v;
+  } else if (ch < D) {
+    hin[r * Fi + (ch - 3)] = z[r * D + ch] * mk;
+  } else {
+    hin[r * Fi + F] = t[b];  // time channel is not masked (en_dynamics.py:66-74)
+  }
+}
+
+// egnn_new.py:197 h = embedding(h); rows of padded nodes are written as 0 (they never reach a real node:
+// every path out of them is cut by edge_mask and each layer ends in *node_mask)
+__global__ void __launch_bounds__(256) embed_k(const float* __restrict__ hin, int Fi, const float* __restrict__ wT,
+                                               const float* __restrict__ bias, const int32_t* __restrict__ sizes,
+                                               int N, float* __restrict__ h) {
+  const int64_t r = blockIdx.x;
+  const int c = threadIdx.x, b = (int)(r / N), i = (int)(r % N);
+  float v = 0.f;
+  if (i < sizes[b]) {
+    v = bias[c];
+    for (int f = 0; f < Fi; ++f) v = fmaf(hin[r * Fi + f], wT[f * H + c], v);
+  }
+  h[r * H + c] = v;
+}
+
+// egnn_new.py:202-204 h = embedding_out(h) * node_mask.  One warp per output feature.
+__global__ void __launch_bounds__(256) out_k(const float* __restrict__ h, const float* __restrict__ w,
+                                             const float* __restrict__ bias, int Fi,
+                                             const int32_t* __restrict__ sizes, int N, float* __restrict__ hout) {
+  const int64_t r = blockIdx.x;
+  const int b = (int)(r / N), i = (int)(r % N), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool real = i < sizes[b];
+  for (int f = warp; f < Fi; f += 8) {
+    float s = 0.f;
+    if (real)
+      for (int c = lane; c < H; c += 32) s = fmaf(h[r * H + c], w[f * H + c], s);
+    s = warp_sum(s);
+    if (lane == 0) hout[r * Fi + f] = real ? s + bias[f] : 0.f;
+  }
+}
+
+// en_dynamics.py:89,103-111: vel = (x_final - x)*mask, drop the time channel, NaN detection.
+__global__ void vel_k(const float* __restrict__ xf, const float* __restrict__ x0, const float* __restrict__ hout,
+                      const int32_t* __restrict__ sizes, int B, int N, int F, float* __restrict__ eps_raw,
+                      int32_t* __restrict__ nanflag) {
+  const int D = 3 + F, Fi = F + 1;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * N * D) return;
+  const int64_t r = idx / D;
+  const int ch = (int)(idx % D), b = (int)(r / N), i = (int)(r % N);
+  float v;
+  if (ch < 3) {
+    v = (xf[r * 3 + ch] - x0[r * 3 + ch]) * (i < sizes[b] ? 1.f : 0.f);
+    if (isnan(v)) atomicOr(nanflag, 1);
+  } else {
+    v = hout[r * Fi + (ch - 3)];
+  }
+  eps_raw[idx] = v;
+}
+
+// masked mean over the nodes of molecule b for the first 3 channels of v [N, D] (models/utils.py:53-56):
+// sum over ALL N rows / n_b.  Called by all threads of a block (>= 96 threads); result valid in all threads.
+__device__ __forceinline__ void block_mean3(const float* v, int N, int D, int n, float* s_mean, float out[3]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 3) {
+    float s = 0.f;
+    for (int i = lane; i < N; i += 32) s += v[i * D + warp];
+    s = warp_sum(s);
+    if (lane == 0) s_mean[warp] = s / (float)n;
+  }
+  __syncthreads();
+  out[0] = s_mean[0];
+  out[1] = s_mean[1];
+  out[2] = s_mean[2];
+  __syncthreads();
+}
+
+// en_dynamics.py:109-116: NaN guard (whole batch) + remove_mean_with_mask; one block per molecule.
+__global__ void __launch_bounds__(128) cog_k(const float* __restrict__ eps_raw, const int32_t* __restrict__ sizes,
+                                             int N, int F, const int32_t* __restrict__ nanflag,
+                                             float* __restrict__ eps, int32_t* __restrict__ flags) {
+  extern __shared__ float sv[];  // [N][D]
+  __shared__ float s_mean[3];
+  const int D = 3 + F, b = blockIdx.x, n = sizes[b];
+  const bool nan = *nanflag != 0;
+  const float* src = eps_raw + (int64_t)b * N * D;
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    float v = src[idx];
+    if (nan && idx % D < 3) v = 0.f;
+    sv[idx] = v;
+  }
+  __syncthreads();
+  float mean[3];
+  block_mean3(sv, N, D, n, s_mean, mean);
+  float* dst = eps + (int64_t)b * N * D;
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    const int i = idx / D, ch = idx % D;
+    float v = sv[idx];
+    if (ch < 3 && i < n) v -= mean[ch];
+    dst[idx] = v;
+  }
+  if (nan && flags && b == 0 && threadIdx.x == 0) atomicOr(flags, HD_FLAG_NAN);
+}
+
+// diffusion_qm9.py:445-456 with the two raw randn draws; one block per molecule.
+__device__ __forceinline__ void load_noise(const float* rx, const float* rh, int N, int F, int n, float* nz,
+                                           float* s_mean) {
+  const int D = 3 + F;
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    const int i = idx / D, ch = idx % D;
+    const float mk = i < n ? 1.f : 0.f;
+    nz[idx] = (ch < 3 ? rx[i * 3 + ch] : rh[i * F + (ch - 3)]) * mk;
+  }
+  __syncthreads();
+  float mean[3];
+  block_mean3(nz, N, D, n, s_mean, mean);
+  for (int idx = threadIdx.x; idx < N * 3; idx += blockDim.x) {
+    const int i = idx / 3, ch = idx % 3;
+    if (i < n) nz[i * D + ch] -= mean[ch];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) combine_noise_k(const float* __restrict__ rx, const float* __restrict__ rh,
+                                                       const int32_t* __restrict__ sizes, int N, int F,
+                                                       float* __restrict__ z) {
+  extern __shared__ float nz[];
+  __shared__ float s_mean[3];
+  const int D = 3 + F, b = blockIdx.x;
+  load_noise(rx + (int64_t)b * N * 3, rh + (int64_t)b * N * F, N, F, sizes[b], nz, s_mean);
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) z[(int64_t)b * N * D + idx] = nz[idx];
+}
+
+// diffusion_qm9.py:328-345; one block per molecule
+__global__ void __launch_bounds__(128) reverse_step_k(const float* __restrict__ zt, const float* __restrict__ eps,
+                                                      const float* __restrict__ rx, const float* __restrict__ rh,
+                                                      const int32_t* __restrict__ sizes, int N, int F,
+                                                      const float* __restrict__ sched, int sched_per_mol,
+                                                      float* __restrict__ zs, int32_t* __restrict__ flags) {
+  extern __shared__ float sm[];  // nz [N*D], ev [N*D], zv [N*D]
+  __shared__ float s_mean[3];
+  __shared__ float s_chk[3];
+  const int D = 3 + F, b = blockIdx.x, n = sizes[b];
+  float* nz = sm;
+  float* ev = sm + N * D;
+  float* zv = ev + N * D;
+  const float* sc = sched + (sched_per_mol ? 3 * b : 0);
+  const float alpha = sc[0], ceps = sc[1], sigma = sc[2];
+  const float* zsrc = zt + (int64_t)b * N * D;
+  const float* esrc = eps + (int64_t)b * N * D;
+  if (threadIdx.x < 3) s_chk[threadIdx.x] = 0.f;
+  load_noise(rx + (int64_t)b * N * 3, rh + (int64_t)b * N * F, N, F, n, nz, s_mean);
+  // assert_mean_zero_with_mask(zt_x) (models/utils.py:65-75), evaluated per molecule
+  float pad_abs = 0.f, max_abs = 0.f;
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    const float v = zsrc[idx];
+    zv[idx] = v;
+    ev[idx] = esrc[idx];
+    if (idx % D < 3) {
+      if (idx / D >= n) pad_abs = fmaxf(pad_abs, fabsf(v));
+      max_abs = fmaxf(max_abs, fabsf(v));
+    }
+  }
+  // float max over non-negative values == max over their int bit patterns
+  atomicMax(reinterpret_cast<int*>(&s_chk[0]), __float_as_int(pad_abs));
+  atomicMax(reinterpret_cast<int*>(&s_chk[1]), __float_as_int(max_abs));
+  __syncthreads();
+  float zsum[3];
+  block_mean3(zv, N, D, 1, s_mean, zsum);  // n=1 -> plain sums
+  if (flags && threadIdx.x == 0) {
+    const float err = fmaxf(fabsf(zsum[0]), fmaxf(fabsf(zsum[1]), fabsf(zsum[2])));
+    int f = 0;
+    if (!(s_chk[0] < 1e-4f)) f |= HD_FLAG_MASK;
+    if (!(err / (s_chk[1] + 1e-10f) < 1e-2f)) f |= HD_FLAG_COG;
+    if (f) atomicOr(flags, f);
+  }
+  float mean[3];
+  block_mean3(ev, N, D, n, s_mean, mean);  // :330 second CoG removal on eps_x
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    const int i = idx / D, ch = idx % D;
+    float e = ev[idx];
+    if (ch < 3 && i < n) e -= mean[ch];
+    const float mu = zv[idx] / alpha - ceps * e;  // :331
+    zv[idx] = mu + sigma * nz[idx];               // :337, :442
+  }
+  __syncthreads();
+  block_mean3(zv, N, D, n, s_mean, mean);  // :340-344
+  float* dst = zs + (int64_t)b * N * D;
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    const int i = idx / D, ch = idx % D;
+    float v = zv[idx];
+    if (ch < 3 && i < n) v -= mean[ch];
+    dst[idx] = v;
+  }
+}
+
+// diffusion_qm9.py:294-310, :174-179
+__global__ void __launch_bounds__(128) final_decode_k(const float* __restrict__ z0, const float* __restrict__ eps0,
+                                                      const float* __restrict__ rx, const float* __restrict__ rh,
+                                                      const int32_t* __restrict__ sizes, int N, int F,
+                                                      const float* __restrict__ sched, int sched_per_mol,
+                                                      float norm_x, float norm_h, float bias_h,
+                                                      float* __restrict__ x, float* __restrict__ h) {
+  extern __shared__ float nz[];
+  __shared__ float s_mean[3];
+  const int D = 3 + F, b = blockIdx.x, n = sizes[b];
+  const float* sc = sched + (sched_per_mol ? 3 * b : 0);
+  const float alpha0 = sc[0], sigma0 = sc[1], sigma_x = sc[2];
+  load_noise(rx + (int64_t)b * N * 3, rh + (int64_t)b * N * F, N, F, n, nz, s_mean);
+  const float* zsrc = z0 + (int64_t)b * N * D;
+  const float* esrc = eps0 + (int64_t)b * N * D;
+  for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
+    const int i = idx / D, ch = idx % D;
+    if (ch < 3) {
+      const float mu = 1.0f / alpha0 * (zsrc[idx] - sigma0 * esrc[idx]);  // :244
+      x[((int64_t)b * N + i) * 3 + ch] = (mu + sigma_x * nz[idx]) * norm_x;
+    } else {
+      h[((int64_t)b * N + i) * F + (ch - 3)] = (zsrc[idx] * norm_h + bias_h) * (i < n ? 1.f : 0.f);
+    }
+  }
+}
+
+__device__ __forceinline__ float softplus_t(float v) { return v > 20.0f ? v : log1pf(expf(v)); }  // F.softplus
+__device__ __forceinline__ float logsigmoid_t(float v) { return fminf(v, 0.0f) - log1pf(expf(-fabsf(v))); }
+__device__ __forceinline__ float sigmoid_t(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__global__ void step_scalars_k(const float* __restrict__ gs, const float* __restrict__ gt, int count,
+                               float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const float s = gs[k], t = gt[k];
+  const float sigma2_ts = -expm1f(softplus_t(s) - softplus_t(t));            // :189-191
+  const float alpha_ts = expf(0.5f * (logsigmoid_t(-t) - logsigmoid_t(-s)));  // :194-200
+  const float sigma_ts = sqrtf(sigma2_ts);
+  const float sigma_s = sqrtf(sigmoid_t(s)), sigma_t = sqrtf(sigmoid_t(t));  // :148-150
+  out[3 * k + 0] = alpha_ts;
+  out[3 * k + 1] = sigma2_ts / alpha_ts / sigma_t;  // :331
+  out[3 * k + 2] = sigma_ts * sigma_s / sigma_t;    // :334
+}
+
+__global__ void final_scalars_k(const float* __restrict__ g0, int count, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const float g = g0[k];
+  out[3 * k + 0] = sqrtf(sigmoid_t(-g));  // alpha_0
+  out[3 * k + 1] = sqrtf(sigmoid_t(g));   // sigma_0
+  out[3 * k + 2] = expf(-(-0.5f * g));    // SNR(-0.5*gamma_0)
+}
+
+__global__ void loop_fetch_k(int32_t* counter, const float* __restrict__ t_table, const float* __restrict__ sched_table,
+                             int B, float* __restrict__ t_cur, float* __restrict__ sched_cur) {
+  const int k = *counter;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) t_cur[b] = t_table[k];
+  if (threadIdx.x < 3) sched_cur[threadIdx.x] = sched_table[3 * k + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) *counter = k + 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// orchestration
+// ---------------------------------------------------------------------------------------
+static int check_common(const hd_config* cfg, const void* packed, const int32_t* sizes, int B, int N, int engine) {
+  if (!cfg || !packed || !sizes) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  if (B < 1 || N < 1 || N > 128) {
+    set_error("unsupported batch shape B=%d N=%d (need B>=1, 1<=N<=128)", B, N);
+    return HD_E_INVALID;
+  }
+  if (engine != HD_ENGINE_FP32 && engine != HD_ENGINE_TC_STRICT && engine != HD_ENGINE_TC_FAST) {
+    set_error("unknown engine %d", engine);
+    return HD_E_INVALID;
+  }
+  return HD_OK;
+}
+
+static int sub_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine) {
+  if (engine == HD_ENGINE_FP32) return fp32_gcl(c, si, h, x, x0);
+  return tc_gcl(c, si, h, x, x0, engine);
+}
+static int sub_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* xo,
+                     int engine) {
+  if (engine == HD_ENGINE_FP32) return fp32_equiv(c, si, h, x, x0, xo);
+  return tc_equiv(c, si, h, x, x0, xo, engine);
+}
+
+// EGNN blocks (egnn_new.py:198-199, :139-152) on ws.h / ws.x; returns the buffer holding the final x
+static int run_blocks(const FwdCtx& c, int engine, float** x_final) {
+  float* h = reinterpret_cast<float*>(c.ws + c.W.h);
+  float* x = reinterpret_cast<float*>(c.ws + c.W.x);
+  float* x2 = reinterpret_cast<float*>(c.ws + c.W.x2);
+  const float* x0 = reinterpret_cast<const float*>(c.ws + c.W.x0);
+  int si = 0, rc;
+  for (int l = 0; l < c.cfg->n_layers; ++l) {
+    for (int s = 0; s < c.cfg->inv_sublayers; ++s)
+      if ((rc = sub_gcl(c, si++, h, x, x0, engine))) return rc;
+    if ((rc = sub_equiv(c, si++, h, x, x0, x2, engine))) return rc;
+    float* tmp = x;
+    x = x2;
+    x2 = tmp;
+  }
+  *x_final = x;
+  return HD_OK;
+}
+
+}  // namespace hd
+
+using namespace hd;
+
+extern "C" {
+
+HD_API int32_t hd_abi_version(void) { return HD_ABI_VERSION; }
+HD_API const char* hd_last_error(void) { return hd::last_error(); }
+HD_API int32_t hd_engine_available(int32_t engine) {
+  if (engine == HD_ENGINE_FP32) return 1;
+  if (engine == HD_ENGINE_TC_STRICT || engine == HD_ENGINE_TC_FAST) return tc_available() ? 1 : 0;
+  return 0;
+}
+
+HD_API int64_t hd_launch_count(void) { return hd::launch_count(); }
+
+HD_API int64_t hd_weight_count(const hd_config* cfg) {
+  Layout L;
+  if (!cfg || !make_layout(*cfg, &L)) return HD_E_INVALID;
+  return L.flat_count;
+}
+
+HD_API int64_t hd_packed_bytes(const hd_config* cfg) {
+  Layout L;
+  if (!cfg || !make_layout(*cfg, &L)) return HD_E_INVALID;
+  return L.total_bytes;
+}
+
+HD_API int32_t hd_pack_weights(const hd_config* cfg, const float* w_flat, void* packed, hd_stream_t stream) {
+  Layout L;
+  if (!cfg || !w_flat || !packed) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  if (!make_layout(*cfg, &L)) return HD_E_INVALID;
+  return pack_weights(*cfg, L, w_flat, static_cast<char*>(packed), static_cast<cudaStream_t>(stream));
+}
+
+HD_API int64_t hd_workspace_bytes(const hd_config* cfg, int32_t B, int32_t N) {
+  if (!cfg || B < 1 || N < 1) return HD_E_INVALID;
+  return make_workspace(*cfg, B, N).total_bytes;
+}
+
+HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, const float* z, const float* t,
+                            const int32_t* sizes, int32_t B, int32_t N, float* eps, void* workspace,
+                            int32_t* flags, int32_t engine, hd_stream_t stream) {
+  int rc = check_common(cfg, packed, sizes, B, N, engine);
+  if (rc) return rc;
+  if (!z || !t || !eps || !workspace) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  Layout L;
+  if (!make_layout(*cfg, &L)) return HD_E_INVALID;
+  FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
+           sizes, B, N, static_cast<cudaStream_t>(stream)};
+  const int Fi = cfg->in_node_nf, F = Fi - 1, D = 3 + F;
+  const int64_t BN = (int64_t)B * N;
+  auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
+  auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  int32_t* nanflag = reinterpret_cast<int32_t*>(c.ws + c.W.nanflag);
+  prep_k<<<(unsigned)((BN * (D + 1) + 255) / 256), 256, 0, c.stream>>>(z, t, sizes, B, N, F, WF(c.W.hin), WF(c.W.x),
+                                                                      WF(c.W.x0), nanflag);
+  HD_CHECK_LAUNCH();
+  embed_k<<<(unsigned)BN, 256, 0, c.stream>>>(WF(c.W.hin), Fi, PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h));
+  HD_CHECK_LAUNCH();
+  float* xf = nullptr;
+  if ((rc = run_blocks(c, engine, &xf))) return rc;
+  out_k<<<(unsigned)BN, 256, 0, c.stream>>>(WF(c.W.h), PF(L.out_w), PF(L.out_b), Fi, sizes, N, WF(c.W.hout));
+  HD_CHECK_LAUNCH();
+  vel_k<<<(unsigned)((BN * D + 255) / 256), 256, 0, c.stream>>>(xf, WF(c.W.x0), WF(c.W.hout), sizes, B, N, F,
+                                                               WF(c.W.eps_raw), nanflag);
+  HD_CHECK_LAUNCH();
+  cog_k<<<B, 128, sizeof(float) * N * D, c.stream>>>(WF(c.W.eps_raw), sizes, N, F, nanflag, eps, flags);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_egnn_forward(const hd_config* cfg, const void* packed, const float* h_in, const float* x_in,
+                        const int32_t* sizes, int32_t B, int32_t N, float* h_out, float* x_out, void* workspace,
+                        int32_t engine, hd_stream_t stream) {
+  int rc = check_common(cfg, packed, sizes, B, N, engine);
+  if (rc) return rc;
+  if (!h_in || !x_in || !h_out || !x_out || !workspace) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  Layout L;
+  if (!make_layout(*cfg, &L)) return HD_E_INVALID;
+  FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
+           sizes, B, N, static_cast<cudaStream_t>(stream)};
+  const int Fi = cfg->in_node_nf;
+  const int64_t BN = (int64_t)B * N;
+  auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
+  auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  HD_CHECK_CUDA(cudaMemcpyAsync(WF(c.W.x), x_in, BN * 3 * 4, cudaMemcpyDeviceToDevice, c.stream));
+  HD_CHECK_CUDA(cudaMemcpyAsync(WF(c.W.x0), x_in, BN * 3 * 4, cudaMemcpyDeviceToDevice, c.stream));
+  embed_k<<<(unsigned)BN, 256, 0, c.stream>>>(h_in, Fi, PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h));
+  HD_CHECK_LAUNCH();
+  float* xf = nullptr;
+  if ((rc = run_blocks(c, engine, &xf))) return rc;
+  out_k<<<(unsigned)BN, 256, 0, c.stream>>>(WF(c.W.h), PF(L.out_w), PF(L.out_b), Fi, sizes, N, h_out);
+  HD_CHECK_LAUNCH();
+  HD_CHECK_CUDA(cudaMemcpyAsync(x_out, xf, BN * 3 * 4, cudaMemcpyDeviceToDevice, c.stream));
+  return HD_OK;
+}
+
+HD_API int32_t hd_gcl_forward(const hd_config* cfg, const void* packed, int32_t block, int32_t sub, float* h,
+                       const float* x, const float* x0, const int32_t* sizes, int32_t B, int32_t N,
+                       void* workspace, int32_t engine, hd_stream_t stream) {
+  int rc = check_common(cfg, packed, sizes, B, N, engine);
+  if (rc) return rc;
+  if (!h || !x || !x0 || !workspace || block < 0 || block >= cfg->n_layers || sub < 0 ||
+      sub >= cfg->inv_sublayers) {
+    set_error("bad argument (block=%d sub=%d)", block, sub);
+    return HD_E_INVALID;
+  }
+  Layout L;
+  if (!make_layout(*cfg, &L)) return HD_E_INVALID;
+  FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
+           sizes, B, N, static_cast<cudaStream_t>(stream)};
+  return sub_gcl(c, block * (cfg->inv_sublayers + 1) + sub, h, x, x0, engine);
+}
+
+HD_API int32_t hd_equiv_update(const hd_config* cfg, const void* packed, int32_t block, const float* h, const float* x,
+                        const float* x0, const int32_t* sizes, int32_t B, int32_t N, float* x_out,
+                        void* workspace, int32_t engine, hd_stream_t stream) {
+  int rc = check_common(cfg, packed, sizes, B, N, engine);
+  if (rc) return rc;
+  if (!h || !x || !x0 || !x_out || x_out == x || !workspace || block < 0 || block >= cfg->n_layers) {
+    set_error("bad argument (block=%d; x_out must not alias x)", block);
+    return HD_E_INVALID;
+  }
+  Layout L;
+  if (!make_layout(*cfg, &L)) return HD_E_INVALID;
+  FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
+           sizes, B, N, static_cast<cudaStream_t>(stream)};
+  return sub_equiv(c, block * (cfg->inv_sublayers + 1) + cfg->inv_sublayers, h, x, x0, x_out, engine);
+}
+
+HD_API int32_t hd_edge_kernel_only(const hd_config* cfg, const void* packed, int32_t block, int32_t sub,
+                                   const float* x, const float* x0, const int32_t* sizes, int32_t B, int32_t N,
+                                   void* workspace, int32_t engine, hd_stream_t stream) {
+  int rc = check_common(cfg, packed, sizes, B, N, engine);
+  if (rc) return rc;
+  if (!x || !x0 || !workspace || block < 0 || block >= cfg->n_layers || sub < 0 || sub > cfg->inv_sublayers) {
+    set_error("bad argument (block=%d sub=%d)", block, sub);
+    return HD_E_INVALID;
+  }
+  Layout L;
+  if (!make_layout(*cfg, &L)) return HD_E_INVALID;
+  FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
+           sizes, B, N, static_cast<cudaStream_t>(stream)};
+  const int si = block * (cfg->inv_sublayers + 1) + sub;
+  if (engine == HD_ENGINE_FP32) return fp32_edge_only(c, si, x, x0);
+  return tc_edge_only(c, si, x, x0, engine);
+}
+
+static int check_mol(const int32_t* sizes, int B, int N, int F) {
+  if (!sizes || B < 1 || N < 1 || N > 1024 || F < 0 || F > 64) {
+    set_error("bad shape B=%d N=%d F=%d", B, N, F);
+    return HD_E_INVALID;
+  }
+  return HD_OK;
+}
+
+HD_API int32_t hd_combine_noise(const float* randn_x, const float* randn_h, const int32_t* sizes, int32_t B, int32_t N,
+                         int32_t F, float* z, hd_stream_t stream) {
+  int rc = check_mol(sizes, B, N, F);
+  if (rc) return rc;
+  combine_noise_k<<<B, 128, sizeof(float) * N * (3 + F), static_cast<cudaStream_t>(stream)>>>(randn_x, randn_h,
+                                                                                              sizes, N, F, z);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_step_scalars(const float* gamma_s, const float* gamma_t, int32_t count, float* sched,
+                        hd_stream_t stream) {
+  if (!gamma_s || !gamma_t || !sched || count < 1) {
+    set_error("bad argument");
+    return HD_E_INVALID;
+  }
+  step_scalars_k<<<(count + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma_s, gamma_t, count,
+                                                                                     sched);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_final_scalars(const float* gamma_0, int32_t count, float* sched, hd_stream_t stream) {
+  if (!gamma_0 || !sched || count < 1) {
+    set_error("bad argument");
+    return HD_E_INVALID;
+  }
+  final_scalars_k<<<(count + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma_0, count, sched);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_reverse_step(const float* zt, const float* eps, const float* randn_x, const float* randn_h,
+                        const int32_t* sizes, int32_t B, int32_t N, int32_t F, const float* sched,
+                        int32_t sched_per_mol, float* zs, int32_t* flags, hd_stream_t stream) {
+  int rc = check_mol(sizes, B, N, F);
+  if (rc) return rc;
+  if (!zt || !eps || !randn_x || !randn_h || !sched || !zs) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  reverse_step_k<<<B, 128, sizeof(float) * 3 * N * (3 + F), static_cast<cudaStream_t>(stream)>>>(
+      zt, eps, randn_x, randn_h, sizes, N, F, sched, sched_per_mol, zs, flags);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* randn_x, const float* randn_h,
+                        const int32_t* sizes, int32_t B, int32_t N, int32_t F, const float* sched,
+                        int32_t sched_per_mol, float norm_x, float norm_h, float bias_h, float* x, float* h,
+                        hd_stream_t stream) {
+  int rc = check_mol(sizes, B, N, F);
+  if (rc) return rc;
+  if (!z0 || !eps0 || !randn_x || !randn_h || !sched || !x || !h) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  final_decode_k<<<B, 128, sizeof(float) * N * (3 + F), static_cast<cudaStream_t>(stream)>>>(
+      z0, eps0, randn_x, randn_h, sizes, N, F, sched, sched_per_mol, norm_x, norm_h, bias_h, x, h);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B, float* t_cur,
+                      float* sched_cur, hd_stream_t stream) {
+  if (!counter || !t_table || !sched_table || !t_cur || !sched_cur || B < 1) {
+    set_error("bad argument");
+    return HD_E_INVALID;
+  }
+  loop_fetch_k<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(counter, t_table, sched_table, B, t_cur,
+                                                                 sched_cur);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// hd_common.cuh - shared declarations of the native library (config, packed-weight layout,
+// workspace layout, device helpers).  Host+device header; no torch types anywhere.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/hierdiff_b200.h"
+
+namespace hd {
+
+constexpr int H = 256;  // hidden_nf this build is specialised for
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define HD_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      hd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return HD_E_CUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define HD_CHECK_LAUNCH()                                                                \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      hd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return HD_E_CUDA;                                                                  \
+    }                                                                                    \
+    hd::count_launch();                                                                  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Packed weight image.  All offsets are BYTES from the start of the packed buffer and are
+// multiples of 256.  One `SubLayer` per edge-MLP sub-layer: inv_sublayers GCLs then one
+// EquivariantUpdate per block.
+// ---------------------------------------------------------------------------------------
+struct SubLayer {
+  bool is_gcl;
+  // sources: float offsets into the flat state_dict-order buffer (-1 = absent)
+  int64_t s_w1, s_b1, s_w2, s_b2, s_v1, s_c1, s_v2, s_c2, s_wa, s_ba;
+  // fp32 images
+  int64_t w1abT;  // [H][2H]  : w1abT[k][o] = W1[o % H][ (o / H) * H + k ]  (o<H: h_i part, o>=H: h_j part)
+  int64_t b1;     // [2H]     : [b1 | 0] (bias of the fused A|B pre-projection)
+  int64_t wr;     // [H]      : W1[:, 2H]   (weight of |x_i-x_j|^2)
+  int64_t wd;     // [H]      : W1[:, 2H+1] (weight of |x0_i-x0_j|^2)
+  int64_t w2T;    // [H][H]   : w2T[k][o] = W2[o][k]
+  int64_t b2;     // [H]
+  int64_t wa;     // [H]      : att_mlp.0.weight (GCL) or coord_mlp.4.weight (equiv)
+  int64_t ba;     // [1] (+pad): att_mlp.0.bias (GCL) or 0
+  int64_t v1T;    // [2H][H]  : GCL only, node_mlp.0 transposed ([h | agg] input order)
+  int64_t c1;     // [H]
+  int64_t v2T;    // [H][H]
+  int64_t c2;     // [H]
+  // tcgen05 operand images (bf16, canonical K-major no-swizzle core-matrix order):
+  //   img[half][kg][n_local][8] with half<2, kg<H/8, n_local<H/2: element = W[half*H/2+n_local][kg*8+e]
+  int64_t w2_hi, w2_lo;        // edge_mlp.2 / coord_mlp.2
+  int64_t w1ab_hi, w1ab_lo;    // [2H out][H k] node pre-projection, 4 quarter images of 128 rows
+  int64_t v1_hi, v1_lo;        // [H out][2H k]  (GCL) two half images, each K=2H
+  int64_t v2_hi, v2_lo;        // [H out][H k]
+};
+
+struct Layout {
+  int64_t s_emb_w, s_emb_b, s_out_w, s_out_b;  // flat offsets
+  int64_t emb_wT;  // [Fi][H]
+  int64_t emb_b;   // [H]
+  int64_t out_w;   // [Fi][H] (as in the state_dict)
+  int64_t out_b;   // [Fi] (+pad)
+  std::vector<SubLayer> subs;
+  int64_t total_bytes;
+  int64_t flat_count;
+};
+
+// returns false (and sets the error) when cfg is not supported by this build
+bool make_layout(const hd_config& cfg, Layout* out);
+
+// ---------------------------------------------------------------------------------------
+// Workspace (bytes offsets, 256-aligned)
+// ---------------------------------------------------------------------------------------
+struct Workspace {
+  int64_t h;      // [BN][H]
+  int64_t ab;     // [BN][2H]   node pre-projection: A_i (bias folded) | B_j
+  int64_t agg;    // [BN][H]
+  int64_t hid;    // [BN][H]
+  int64_t x;      // [BN][3]
+  int64_t x2;     // [BN][3]    ping-pong for the coordinate update
+  int64_t x0;     // [BN][3]    EGNN-entry coordinates
+  int64_t hin;    // [BN][Fi]
+  int64_t hout;   // [BN][Fi]
+  int64_t eps_raw;// [BN][3+F]
+  int64_t nanflag;// [1] int32 per forward
+  int64_t total_bytes;
+};
+Workspace make_workspace(const hd_config& cfg, int B, int N);
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+// SiLU as the reference evaluates it, v * sigmoid(v) (ATen: x / (1 + exp(-x)))
+__device__ __forceinline__ float silu_acc(float v) { return v / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+// engine entry points (hd_fp32.cu / hd_tc.cu) ------------------------------------------------
+struct FwdCtx {
+  const hd_config* cfg;
+  const Layout* L;
+  const char* packed;
+  char* ws;
+  Workspace W;
+  const int32_t* sizes;
+  int B, N;
+  cudaStream_t stream;
+};
+
+// GCL sub-layer `si` (index into L.subs) in place on ctx.ws h; reads x (ws.x) and x0.
+int fp32_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0);
+int fp32_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out);
+int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine);
+int tc_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out, int engine);
+// edge kernel alone on ws.ab (profiling hook); output into ws.agg (GCL) / ws.x2 (equiv)
+int fp32_edge_only(const FwdCtx& c, int si, const float* x, const float* x0);
+int tc_edge_only(const FwdCtx& c, int si, const float* x, const float* x0, int engine);
+bool tc_available();
+
+}  // namespace hd

@@ -1,0 +1,233 @@
+// hd_layout.cu - packed-weight and workspace layouts, error string, weight packing kernels.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include <cuda_bf16.h>
+
+#include "hd_common.cuh"
+
+namespace hd {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+static int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+bool make_layout(const hd_config& c, Layout* out) {
+  if (c.hidden_nf != H) {
+    set_error("hidden_nf=%d unsupported: this build is specialised for hidden_nf=%d", c.hidden_nf, H);
+    return false;
+  }
+  if (c.n_layers < 1 || c.n_layers > 64 || c.inv_sublayers < 1 || c.inv_sublayers > 8 || c.in_node_nf < 1 ||
+      c.in_node_nf > 64) {
+    set_error("bad config: n_layers=%d inv_sublayers=%d in_node_nf=%d", c.n_layers, c.inv_sublayers, c.in_node_nf);
+    return false;
+  }
+  if (!(c.normalization_factor > 0.f)) {
+    set_error("normalization_factor must be > 0");
+    return false;
+  }
+  Layout& L = *out;
+  L.subs.clear();
+  const int64_t Fi = c.in_node_nf;
+  int64_t s = 0;  // flat cursor (floats)
+  auto take = [&](int64_t n) {
+    int64_t r = s;
+    s += n;
+    return r;
+  };
+  L.s_emb_w = take(H * Fi);
+  L.s_emb_b = take(H);
+  L.s_out_w = take(Fi * H);
+  L.s_out_b = take(Fi);
+  int64_t p = 0;  // packed cursor (bytes)
+  auto put = [&](int64_t bytes) {
+    int64_t r = p;
+    p = align256(p + bytes);
+    return r;
+  };
+  L.emb_wT = put(Fi * H * 4);
+  L.emb_b = put(H * 4);
+  L.out_w = put(Fi * H * 4);
+  L.out_b = put(Fi * 4);
+  for (int b = 0; b < c.n_layers; ++b) {
+    for (int k = 0; k <= c.inv_sublayers; ++k) {
+      SubLayer S{};
+      S.is_gcl = k < c.inv_sublayers;
+      S.s_w1 = take((int64_t)H * (2 * H + 2));
+      S.s_b1 = take(H);
+      S.s_w2 = take((int64_t)H * H);
+      S.s_b2 = take(H);
+      S.s_v1 = S.s_c1 = S.s_v2 = S.s_c2 = S.s_ba = -1;
+      if (S.is_gcl) {
+        S.s_v1 = take((int64_t)H * 2 * H);
+        S.s_c1 = take(H);
+        S.s_v2 = take((int64_t)H * H);
+        S.s_c2 = take(H);
+        if (c.attention) {
+          S.s_wa = take(H);
+          S.s_ba = take(1);
+        } else {
+          S.s_wa = -1;
+        }
+      } else {
+        S.s_wa = take(H);
+      }
+      S.w1abT = put((int64_t)H * 2 * H * 4);
+      S.b1 = put(2 * H * 4);  // [b1 | 0]
+      S.wr = put(H * 4);
+      S.wd = put(H * 4);
+      S.w2T = put((int64_t)H * H * 4);
+      S.b2 = put(H * 4);
+      S.wa = put(H * 4);
+      S.ba = put(16);
+      if (S.is_gcl) {
+        S.v1T = put((int64_t)2 * H * H * 4);
+        S.c1 = put(H * 4);
+        S.v2T = put((int64_t)H * H * 4);
+        S.c2 = put(H * 4);
+      } else {
+        S.v1T = S.c1 = S.v2T = S.c2 = -1;
+      }
+      S.w2_hi = put((int64_t)H * H * 2);
+      S.w2_lo = put((int64_t)H * H * 2);
+      S.w1ab_hi = put((int64_t)2 * H * H * 2);
+      S.w1ab_lo = put((int64_t)2 * H * H * 2);
+      if (S.is_gcl) {
+        S.v1_hi = put((int64_t)2 * H * H * 2);
+        S.v1_lo = put((int64_t)2 * H * H * 2);
+        S.v2_hi = put((int64_t)H * H * 2);
+        S.v2_lo = put((int64_t)H * H * 2);
+      } else {
+        S.v1_hi = S.v1_lo = S.v2_hi = S.v2_lo = -1;
+      }
+      L.subs.push_back(S);
+    }
+  }
+  L.total_bytes = p;
+  L.flat_count = s;
+  return true;
+}
+
+Workspace make_workspace(const hd_config& c, int B, int N) {
+  Workspace W{};
+  const int64_t BN = (int64_t)B * N, Fi = c.in_node_nf;
+  int64_t p = 0;
+  auto put = [&](int64_t bytes) {
+    int64_t r = p;
+    p = align256(p + bytes);
+    return r;
+  };
+  W.h = put(BN * H * 4);
+  W.ab = put(BN * 2 * H * 4);
+  W.agg = put(BN * H * 4);
+  W.hid = put(BN * H * 4);
+  W.x = put(BN * 3 * 4);
+  W.x2 = put(BN * 3 * 4);
+  W.x0 = put(BN * 3 * 4);
+  W.hin = put(BN * Fi * 4);
+  W.hout = put(BN * Fi * 4);
+  W.eps_raw = put(BN * (3 + Fi) * 4);
+  W.nanflag = put(256);
+  W.total_bytes = p;
+  return W;
+}
+
+// ---------------------------------------------------------------------------------------
+// packing kernels
+// ---------------------------------------------------------------------------------------
+// dst[k*n_out + o] = src[o*ld + col0 + k]   (k < n_k, o < n_out)
+__global__ void transpose_k(const float* __restrict__ src, int ld, int col0, int n_out, int n_k,
+                            float* __restrict__ dst, int dst_ld, int dst_col0) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out * n_k) return;
+  int k = idx / n_out, o = idx % n_out;
+  dst[(int64_t)k * dst_ld + dst_col0 + o] = src[(int64_t)o * ld + col0 + k];
+}
+// dst[o] = src[o*ld + col]
+__global__ void column_k(const float* __restrict__ src, int ld, int col, int n, float* __restrict__ dst) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < n) dst[o] = src[(int64_t)o * ld + col];
+}
+__global__ void copy_k(const float* __restrict__ src, int n, float* __restrict__ dst) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < n) dst[o] = src ? src[o] : 0.f;
+}
+// bf16 hi/lo operand image of rows [row0, row0+rows) x K columns [col0, col0+K) of src (ld):
+// img[kg][r][e] (kg < K/8, r < rows, e < 8)
+__global__ void image_k(const float* __restrict__ src, int ld, int row0, int col0, int rows, int K,
+                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * K) return;
+  int e = idx & 7, r = (idx >> 3) % rows, kg = (idx >> 3) / rows;
+  float v = src[(int64_t)(row0 + r) * ld + col0 + kg * 8 + e];
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, cudaStream_t st) {
+  const int T = 256;
+  auto grid = [&](int64_t n) { return (unsigned)((n + T - 1) / T); };
+  auto F = [&](int64_t off) { return reinterpret_cast<float*>(P + off); };
+  auto BF = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(P + off); };
+  const int Fi = c.in_node_nf;
+  transpose_k<<<grid(H * Fi), T, 0, st>>>(w + L.s_emb_w, Fi, 0, H, Fi, F(L.emb_wT), H, 0);
+  copy_k<<<grid(H), T, 0, st>>>(w + L.s_emb_b, H, F(L.emb_b));
+  copy_k<<<grid(Fi * H), T, 0, st>>>(w + L.s_out_w, Fi * H, F(L.out_w));
+  copy_k<<<grid(Fi), T, 0, st>>>(w + L.s_out_b, Fi, F(L.out_b));
+  for (const SubLayer& S : L.subs) {
+    const int ld1 = 2 * H + 2;
+    transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_w1, ld1, 0, H, H, F(S.w1abT), 2 * H, 0);
+    transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_w1, ld1, H, H, H, F(S.w1abT), 2 * H, H);
+    copy_k<<<grid(H), T, 0, st>>>(w + S.s_b1, H, F(S.b1));
+    copy_k<<<grid(H), T, 0, st>>>(nullptr, H, F(S.b1) + H);
+    column_k<<<grid(H), T, 0, st>>>(w + S.s_w1, ld1, 2 * H, H, F(S.wr));
+    column_k<<<grid(H), T, 0, st>>>(w + S.s_w1, ld1, 2 * H + 1, H, F(S.wd));
+    transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_w2, H, 0, H, H, F(S.w2T), H, 0);
+    copy_k<<<grid(H), T, 0, st>>>(w + S.s_b2, H, F(S.b2));
+    copy_k<<<grid(H), T, 0, st>>>(S.s_wa >= 0 ? w + S.s_wa : nullptr, H, F(S.wa));
+    copy_k<<<1, T, 0, st>>>(S.s_ba >= 0 ? w + S.s_ba : nullptr, 1, F(S.ba));
+    // tensor-core images: W2 as two N-halves of 128 rows, K = H
+    for (int half = 0; half < 2; ++half) {
+      const int64_t o = (int64_t)half * (H / 2) * H;  // elements
+      image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_w2, H, half * (H / 2), 0, H / 2, H, BF(S.w2_hi) + o,
+                                             BF(S.w2_lo) + o);
+    }
+    // W1ab as four 128-row quarters: rows 0..255 = h_i part (cols 0..H), rows 256..511 = h_j part
+    for (int q = 0; q < 4; ++q) {
+      const int64_t o = (int64_t)q * (H / 2) * H;
+      const int part = q / 2, row0 = (q % 2) * (H / 2);
+      image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_w1, ld1, row0, part * H, H / 2, H, BF(S.w1ab_hi) + o,
+                                             BF(S.w1ab_lo) + o);
+    }
+    if (S.is_gcl) {
+      transpose_k<<<grid(2 * H * H), T, 0, st>>>(w + S.s_v1, 2 * H, 0, H, 2 * H, F(S.v1T), H, 0);
+      copy_k<<<grid(H), T, 0, st>>>(w + S.s_c1, H, F(S.c1));
+      transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_v2, H, 0, H, H, F(S.v2T), H, 0);
+      copy_k<<<grid(H), T, 0, st>>>(w + S.s_c2, H, F(S.c2));
+      for (int half = 0; half < 2; ++half) {
+        const int64_t o1 = (int64_t)half * (H / 2) * 2 * H, o2 = (int64_t)half * (H / 2) * H;
+        image_k<<<grid(H / 2 * 2 * H), T, 0, st>>>(w + S.s_v1, 2 * H, half * (H / 2), 0, H / 2, 2 * H,
+                                                   BF(S.v1_hi) + o1, BF(S.v1_lo) + o1);
+        image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_v2, H, half * (H / 2), 0, H / 2, H, BF(S.v2_hi) + o2,
+                                               BF(S.v2_lo) + o2);
+      }
+    }
+  }
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+}  // namespace hd

@@ -1,0 +1,285 @@
+"""Host-side mirror of ``endiffusion/train_module/diffusion_qm9.py`` - the SAMPLING half of ``DiffusionQM9``.
+
+Same constructor (``DiffusionQM9(cfg)``, diffusion_qm9.py:37-115), same ``state_dict`` keys, same
+``sample`` / ``sample_batches`` / ``sample_p_zs_given_zt`` / ``sample_p_xh_given_z0`` signatures and return
+layout.  Training (loss, optimiser hooks, diffusion_qm9.py:460-879) is out of scope and absent.
+The arithmetic runs in the native library; this file is plumbing: configuration, RNG draws in the
+reference's order, schedule tables, result packaging.
+"""
+import os
+
+import torch
+import torch.nn.functional as F
+import yaml
+from torch import nn
+
+from . import native
+from .distributions import DistributionNodes
+from .dynamics import EGNN_dynamics_QM9
+from .noise_model import GammaNetwork, PredefinedNoiseSchedule
+from .sampling import SamplingLoop, ScheduleTable
+from .utils import check_edge_mask, sizes_from_node_mask
+
+
+def _get(cfg, key, default=None):
+    try:
+        return cfg[key]
+    except (KeyError, AttributeError, TypeError):
+        return getattr(cfg, key, default)
+
+
+class DiffusionQM9(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cwd = "../../../../../../"   # the reference resolves cfg.analyze from its hydra run dir (:39)
+        self.cfg = cfg
+        self.pocket = cfg.pocket
+        if self.pocket:
+            raise NotImplementedError("pocket-conditioned sampling (cfg.pocket) is not built yet")
+        self.node_coarse_type = cfg["node_coarse_type"]
+        if self.node_coarse_type == "prop":
+            self.in_node_nf = 8
+        elif self.node_coarse_type == "elem":
+            self.in_node_nf = 3
+        else:
+            raise NotImplementedError("node_coarse_type should be prop or elem")
+        cfg.dynamics["in_node_nf"] = self.in_node_nf          # the reference mutates cfg here too (:47)
+        assert cfg.loss_type in {"vlb", "l2"}
+        self.loss_type = cfg.loss_type
+        self.include_charges = cfg.include_charges
+        if cfg.noise_schedule == "learned":
+            assert cfg.loss_type == "vlb", "A noise schedule can only be learned with a vlb objective."
+        assert cfg.parametrization == "eps"
+        if cfg.noise_schedule == "learned":
+            self.gamma = GammaNetwork()
+        else:
+            self.gamma = PredefinedNoiseSchedule(**cfg.pre_noise)
+        self.remove_h = cfg.dataset == "qm9"
+        self.hcontinous = cfg.hcontinous
+        if cfg.dynamics.condition_time:
+            cfg.dynamics["in_node_nf"] += 1
+        else:
+            print("Warning: dynamics model is _not_ conditioned on time.")
+        self.dynamics = EGNN_dynamics_QM9(**cfg.dynamics)
+        self.n_dims = cfg.dynamics.n_dims
+        self.num_classes = self.in_node_nf - self.include_charges
+        self.T = cfg.timesteps
+        self.parametrization = cfg.parametrization
+        self.norm_values = cfg.norm_values
+        self.norm_biases = cfg.norm_biases
+        self.register_buffer("buffer", torch.zeros(1))
+        if cfg.noise_schedule != "learned":
+            self.check_issues_norm_values()
+        self.data_augmentation = cfg.data_augmentation
+        with open(self._resolve(cfg.analyze)) as f:
+            histogram = yaml.safe_load(f)
+        self.nodes_dist = DistributionNodes(histogram=histogram)
+        # native-path state
+        self.steps_per_graph = int(_get(cfg, "steps_per_graph", 8) or 8)
+        self.use_cuda_graph = bool(_get(cfg, "use_cuda_graph", True))
+        self._loops = {}
+        self._table = None
+        self._table_key = None
+        self.last_sample_stats = {}
+
+    # ------------------------------------------------------------------ configuration helpers
+    def _resolve(self, path):
+        cands = [path, os.path.join(self.cwd, path)]
+        root = _get(self.cfg, "config_root")
+        if root:
+            cands += [os.path.join(root, path), os.path.join(os.path.dirname(root), path)]
+        for c in cands:
+            if os.path.exists(c):
+                return c
+        raise FileNotFoundError(f"cfg.analyze={path!r} not found (tried {cands})")
+
+    @property
+    def engine(self):
+        return self.dynamics.egnn.engine
+
+    @engine.setter
+    def engine(self, name):
+        if name not in native.ENGINES:
+            raise ValueError(f"engine must be one of {sorted(native.ENGINES)}")
+        if name != self.dynamics.egnn.engine:
+            self._loops = {}   # captured graphs embed the engine's kernels
+        self.dynamics.egnn.engine = name
+
+    def check_issues_norm_values(self, num_stdevs=8):
+        """diffusion_qm9.py:117-132."""
+        zeros = torch.zeros((1, 1))
+        sigma_0 = self.sigma(self.gamma(zeros), target_tensor=zeros).item()
+        max_norm_value = max(self.norm_values[1], self.norm_values[2])
+        if sigma_0 * num_stdevs > 1.0 / max_norm_value:
+            raise ValueError(f"Value for normalization value {max_norm_value} probably too large with sigma_0 "
+                             f"{sigma_0:.5f} and 1 / norm_value = {1. / max_norm_value}")
+
+    # ------------------------------------------------------------------ schedule algebra (:140-204)
+    def phi(self, x, t, node_mask, edge_mask, context, mol_shape=None):
+        return self.dynamics._forward(t, x, node_mask, edge_mask, context, mol_shape)
+
+    def inflate_batch_array(self, array, target):
+        return array.view((array.size(0),) + (1,) * (target.dim() - 1))
+
+    def sigma(self, gamma, target_tensor):
+        return self.inflate_batch_array(torch.sqrt(torch.sigmoid(gamma)), target_tensor)
+
+    def alpha(self, gamma, target_tensor):
+        return self.inflate_batch_array(torch.sqrt(torch.sigmoid(-gamma)), target_tensor)
+
+    def SNR(self, gamma):
+        return torch.exp(-gamma)
+
+    def sigma_and_alpha_t_given_s(self, gamma_t, gamma_s, target_tensor):
+        sigma2 = self.inflate_batch_array(-torch.expm1(F.softplus(gamma_s) - F.softplus(gamma_t)), target_tensor)
+        log_a2 = F.logsigmoid(-gamma_t) - F.logsigmoid(-gamma_s)
+        alpha = self.inflate_batch_array(torch.exp(0.5 * log_a2), target_tensor)
+        return sigma2, torch.sqrt(sigma2), alpha
+
+    def unnormalize(self, x, h, node_mask):
+        return x * self.norm_values[0], (h * self.norm_values[1] + self.norm_biases[1]) * node_mask
+
+    # ------------------------------------------------------------------ eager single-step API
+    def _masks_to_sizes(self, node_mask, edge_mask):
+        B, N = node_mask.shape[0], node_mask.shape[1]
+        sizes = sizes_from_node_mask(node_mask, B, N)
+        if edge_mask is not None:
+            check_edge_mask(edge_mask, sizes, B, N)
+        return sizes
+
+    def _raise_on_flags(self, flags):
+        v = int(flags.item())
+        if v & native.FLAG_NAN:
+            print("Warning: detected nan, resetting EGNN output to zero.")   # en_dynamics.py:109-111
+        if v & native.FLAG_MASK:
+            raise AssertionError("Variables not masked properly.")            # models/utils.py:72-75
+        if v & native.FLAG_COG:
+            raise AssertionError("Mean is not zero")                          # models/utils.py:65-70
+        return v
+
+    def _draw(self, B, N, device):
+        """The two raw draws of sample_combined_position_feature_noise, in the reference's order (:449-454)."""
+        rx = torch.randn((B, N, self.n_dims), device=device)
+        rh = torch.randn((B, N, self.in_node_nf), device=device)
+        return rx, rh
+
+    def sample_combined_position_feature_noise(self, n_samples, n_nodes, node_mask):
+        """diffusion_qm9.py:445-456."""
+        native.require_cuda(node_mask)
+        sizes = sizes_from_node_mask(node_mask, n_samples, n_nodes)
+        rx, rh = self._draw(n_samples, n_nodes, node_mask.device)
+        z = torch.empty(n_samples, n_nodes, self.n_dims + self.in_node_nf, device=node_mask.device)
+        with torch.cuda.device(z.device):
+            native.check(native.lib().hd_combine_noise(native.ptr(rx), native.ptr(rh), native.ptr(sizes), n_samples,
+                                                       n_nodes, self.in_node_nf, native.ptr(z), native.stream_ptr()),
+                         "hd_combine_noise")
+        return z
+
+    def sample_normal(self, mu, sigma, node_mask, fix_noise=False):
+        """diffusion_qm9.py:438-442."""
+        if fix_noise:
+            raise NotImplementedError("fix_noise=True is not built")
+        return mu + sigma * self.sample_combined_position_feature_noise(mu.size(0), mu.size(1), node_mask)
+
+    @torch.no_grad()
+    def sample_p_zs_given_zt(self, s, t, zt, node_mask, edge_mask, context, fix_noise=False, mol_shape=None):
+        """diffusion_qm9.py:312-345: one ancestral step, eager (per-molecule schedule rows like the reference)."""
+        if context is not None or fix_noise:
+            raise NotImplementedError("context / fix_noise are not built")
+        B, N, _ = zt.shape
+        if mol_shape is not None and mol_shape != N:
+            raise NotImplementedError("pocket conditioning (mol_shape < n_nodes) is not built yet")
+        L = native.lib()
+        sizes = self._masks_to_sizes(node_mask, edge_mask)
+        gamma_s = self.gamma(s).reshape(-1).float().contiguous()
+        gamma_t = self.gamma(t).reshape(-1).float().contiguous()
+        sched = torch.empty(B, 3, device=zt.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=zt.device)
+        zt = zt.contiguous().float()
+        eps = self.dynamics.forward_sizes(t, zt, sizes, flags=flags)
+        rx, rh = self._draw(B, N, zt.device)
+        zs = torch.empty_like(zt)
+        with torch.cuda.device(zt.device):
+            st = native.stream_ptr()
+            native.check(L.hd_step_scalars(native.ptr(gamma_s), native.ptr(gamma_t), B, native.ptr(sched), st),
+                         "hd_step_scalars")
+            native.check(L.hd_reverse_step(native.ptr(zt), native.ptr(eps), native.ptr(rx), native.ptr(rh),
+                                           native.ptr(sizes), B, N, self.in_node_nf, native.ptr(sched), 1,
+                                           native.ptr(zs), native.ptr(flags), st), "hd_reverse_step")
+        self._raise_on_flags(flags)
+        return zs
+
+    @torch.no_grad()
+    def sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise=False):
+        """diffusion_qm9.py:294-310."""
+        if context is not None or fix_noise:
+            raise NotImplementedError("context / fix_noise are not built")
+        B, N, _ = z0.shape
+        L = native.lib()
+        sizes = self._masks_to_sizes(node_mask, edge_mask)
+        zeros = torch.zeros(B, 1, device=z0.device)
+        gamma_0 = self.gamma(zeros).reshape(-1).float().contiguous()
+        sched = torch.empty(B, 3, device=z0.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=z0.device)
+        z0 = z0.contiguous().float()
+        eps = self.dynamics.forward_sizes(zeros, z0, sizes, flags=flags)
+        rx, rh = self._draw(B, N, z0.device)
+        x = torch.empty(B, N, self.n_dims, device=z0.device)
+        h = torch.empty(B, N, self.in_node_nf, device=z0.device)
+        with torch.cuda.device(z0.device):
+            st = native.stream_ptr()
+            native.check(L.hd_final_scalars(native.ptr(gamma_0), B, native.ptr(sched), st), "hd_final_scalars")
+            native.check(L.hd_final_decode(native.ptr(z0), native.ptr(eps), native.ptr(rx), native.ptr(rh),
+                                           native.ptr(sizes), B, N, self.in_node_nf, native.ptr(sched), 1,
+                                           float(self.norm_values[0]), float(self.norm_values[1]),
+                                           float(self.norm_biases[1]), native.ptr(x), native.ptr(h), st),
+                         "hd_final_decode")
+        self._raise_on_flags(flags)
+        return x, h
+
+    # ------------------------------------------------------------------ the sampler
+    def schedule_table(self, device):
+        key = (str(device), self.T) + tuple((p.data_ptr(), p._version) for p in self.gamma.parameters())
+        if key != self._table_key:
+            self._table, self._table_key = ScheduleTable(self.gamma, self.T, device), key
+        return self._table
+
+    def sampling_loop(self, B, N, device):
+        key = (B, N, str(device), self.engine, self.use_cuda_graph, self.steps_per_graph)
+        if key not in self._loops:
+            self._loops[key] = SamplingLoop(self, B, N, device, steps_per_graph=self.steps_per_graph,
+                                            use_graph=self.use_cuda_graph)
+        loop = self._loops[key]
+        loop.prepare(self.schedule_table(device))
+        return loop
+
+    @torch.no_grad()
+    def sample_padded(self, sample_n, device, z_T=None):
+        """The chain for given molecule sizes; returns padded CPU tensors x [B,N,3], h [B,N,F]."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise native.NativeError("sampling runs on a CUDA device only (no CPU fallback)")
+        B, N = len(sample_n), max(sample_n)
+        loop = self.sampling_loop(B, N, device)
+        x, h, flags = loop.run(sample_n, z_T=z_T)
+        out = torch.cat([x.reshape(B * N, -1), h.reshape(B * N, -1)], dim=1).cpu()   # one D2H (syncs)
+        self._raise_on_flags(flags)
+        return out[:, :self.n_dims].reshape(B, N, -1), out[:, self.n_dims:].reshape(B, N, -1)
+
+    @torch.no_grad()
+    def sample(self, num_samples, device, context=None, pocket_cond=None):
+        """diffusion_qm9.py:347-395: list of {'x': [n_i,3], 'h': [n_i,F]} CPU tensors."""
+        if context is not None or pocket_cond is not None:
+            raise NotImplementedError("context / pocket conditioning are not built yet")
+        sample_n = self.nodes_dist.sample(num_samples)
+        x, h = self.sample_padded(sample_n, device)
+        return [{"x": x[i, :n].clone(), "h": h[i, :n].clone()} for i, n in enumerate(sample_n)]
+
+    def sample_batches(self, batch_size, num_batches, device, context_range=None, protein_data_all=None):
+        """diffusion_qm9.py:397-436: ``(results, test_names)``."""
+        if protein_data_all is not None or context_range is not None:
+            raise NotImplementedError("protein / context conditioned sampling is not built yet")
+        results, test_names = [], []
+        for _ in range(num_batches):
+            results.extend(self.sample(batch_size, device))
+        return results, test_names

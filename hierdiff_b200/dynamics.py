@@ -1,0 +1,101 @@
+"""Host-side mirror of ``endiffusion/models/module/en_dynamics.py`` (EGNN_dynamics_QM9).
+
+``_forward`` keeps the reference signature (en_dynamics.py:49) and returns the same
+``[B, N, 3+F]`` tensor, but runs as one native call (``hd_dynamics_forward``): masking, time
+concatenation, the EGNN stack, the velocity, the NaN guard and the centre-of-gravity projection
+all happen on the device without host synchronisation.
+"""
+import torch
+from torch import nn
+
+from . import native
+from .egnn import EGNN
+from .utils import check_edge_mask, sizes_from_node_mask
+
+
+class EGNN_dynamics_QM9(nn.Module):
+    """Same constructor as en_dynamics.py:9-36.  Only ``mode='egnn_dynamics'`` is built."""
+
+    def __init__(self, in_node_nf, context_node_nf, n_dims, hidden_nf=64, act_fn="silu", n_layers=4,
+                 attention=False, condition_time=True, tanh=False, mode="egnn_dynamics", norm_constant=0,
+                 inv_sublayers=2, sin_embedding=False, normalization_factor=100, aggregation_method="sum"):
+        super().__init__()
+        if mode != "egnn_dynamics":
+            raise NotImplementedError(f"mode={mode!r}: only 'egnn_dynamics' (the shipped config) is built")
+        if n_dims != 3:
+            raise NotImplementedError("n_dims must be 3")
+        if context_node_nf:
+            raise NotImplementedError("context conditioning (context_node_nf > 0) is not built yet")
+        if not condition_time:
+            raise NotImplementedError("condition_time=False is not built")
+        self.mode = mode
+        self.egnn = EGNN(in_node_nf=in_node_nf + context_node_nf, in_edge_nf=1, hidden_nf=hidden_nf, act_fn=act_fn,
+                         n_layers=n_layers, attention=attention, tanh=tanh, norm_constant=norm_constant,
+                         inv_sublayers=inv_sublayers, sin_embedding=sin_embedding,
+                         normalization_factor=normalization_factor, aggregation_method=aggregation_method)
+        self.in_node_nf = in_node_nf
+        self.context_node_nf = context_node_nf
+        self.n_dims = n_dims
+        self._edges_dict = {}
+        self.condition_time = condition_time
+        self.last_flags = None
+
+    def forward(self, t, xh, node_mask, edge_mask, context=None):
+        raise NotImplementedError  # as the reference (en_dynamics.py:38-39)
+
+    def wrap_forward(self, node_mask, edge_mask, context):
+        def fwd(time, state):
+            return self._forward(time, state, node_mask, edge_mask, context)
+        return fwd
+
+    def unwrap_forward(self):
+        return self._forward
+
+    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None):
+        """``_forward`` with the masks already reduced to ``sizes`` [B] int32 (no validation, no sync)."""
+        native.require_cuda(xh)
+        B, N, D = xh.shape
+        assert D == self.n_dims + self.in_node_nf - 1, (D, self.in_node_nf)
+        xh = xh.contiguous().float()
+        t = t.reshape(-1).float()
+        if t.numel() == 1:
+            t = t.expand(B)
+        t = t.contiguous()
+        eps = torch.empty_like(xh) if out is None else out
+        egnn = self.egnn
+        with torch.cuda.device(xh.device):
+            native.check(native.lib().hd_dynamics_forward(
+                egnn.hd_config(), native.ptr(egnn.packed_weights()), native.ptr(xh), native.ptr(t),
+                native.ptr(sizes), B, N, native.ptr(eps), native.ptr(egnn.workspace(B, N, xh.device)),
+                native.ptr(flags), egnn.engine_id(engine), native.stream_ptr()), "hd_dynamics_forward")
+        return eps
+
+    def _forward(self, t, xh, node_mask, edge_mask, context, mol_shape=None):
+        """en_dynamics.py:49-122."""
+        if context is not None:
+            raise NotImplementedError("context conditioning is not built yet")
+        B, N, _ = xh.shape
+        if mol_shape is not None and mol_shape != N:
+            raise NotImplementedError("pocket conditioning (mol_shape < n_nodes) is not built yet")
+        sizes = sizes_from_node_mask(node_mask, B, N)
+        check_edge_mask(edge_mask, sizes, B, N)
+        flags = torch.zeros(1, dtype=torch.int32, device=xh.device)
+        eps = self.forward_sizes(t, xh, sizes, flags=flags)
+        self.last_flags = flags  # checked lazily: reading it here would force a host sync per call
+        return eps
+
+    def nan_guard_fired(self):
+        """True when the last `_forward` hit the NaN guard of en_dynamics.py:109-111 (host sync)."""
+        fired = self.last_flags is not None and bool(self.last_flags.item() & native.FLAG_NAN)
+        if fired:
+            print("Warning: detected nan, resetting EGNN output to zero.")
+        return fired
+
+    def get_adj_matrix(self, n_nodes, batch_size):
+        """en_dynamics.py:124-143: dense (row, col) lists, b-major / i-major / j-minor (cached, CPU int64)."""
+        key = (n_nodes, batch_size)
+        if key not in self._edges_dict:
+            e = torch.arange(batch_size * n_nodes * n_nodes)
+            b = e // (n_nodes * n_nodes)
+            self._edges_dict[key] = [b * n_nodes + (e // n_nodes) % n_nodes, b * n_nodes + e % n_nodes]
+        return self._edges_dict[key]

@@ -1,0 +1,118 @@
+"""ctypes binding of the C ABI in ``include/hierdiff_b200.h``.
+
+The product path has NO fallback: if the shared library is missing or a call fails, this
+module raises.  (``python -m hierdiff_b200.build`` / ``__graft_entry__.build()`` compile it.)
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libhierdiff_b200.so")
+
+ENGINE_FP32 = 0
+ENGINE_TC_STRICT = 1
+ENGINE_TC_FAST = 2
+ENGINES = {"fp32": ENGINE_FP32, "strict": ENGINE_TC_STRICT, "fast": ENGINE_TC_FAST}
+
+FLAG_NAN = 1
+FLAG_COG = 2
+FLAG_MASK = 4
+
+ABI_VERSION = 1
+
+
+class HdConfig(ctypes.Structure):
+    """``hd_config`` (EGNN hyper-parameters, egnn_new.py:156-190)."""
+    _fields_ = [("n_layers", ctypes.c_int32), ("inv_sublayers", ctypes.c_int32),
+                ("hidden_nf", ctypes.c_int32), ("in_node_nf", ctypes.c_int32),
+                ("attention", ctypes.c_int32), ("tanh", ctypes.c_int32),
+                ("coords_range", ctypes.c_float), ("norm_constant", ctypes.c_float),
+                ("normalization_factor", ctypes.c_float), ("aggregation_mean", ctypes.c_int32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int32
+_F = ctypes.c_float
+_CFG = ctypes.POINTER(HdConfig)
+
+# name -> (restype, argtypes); mirrors include/hierdiff_b200.h one to one
+SIGNATURES = {
+    "hd_abi_version": (_I, []),
+    "hd_last_error": (ctypes.c_char_p, []),
+    "hd_engine_available": (_I, [_I]),
+    "hd_launch_count": (ctypes.c_int64, []),
+    "hd_edge_kernel_only": (_I, [_CFG, _P, _I, _I, _P, _P, _P, _I, _I, _P, _I, _P]),
+    "hd_weight_count": (ctypes.c_int64, [_CFG]),
+    "hd_packed_bytes": (ctypes.c_int64, [_CFG]),
+    "hd_pack_weights": (_I, [_CFG, _P, _P, _P]),
+    "hd_workspace_bytes": (ctypes.c_int64, [_CFG, _I, _I]),
+    "hd_dynamics_forward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P]),
+    "hd_egnn_forward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P]),
+    "hd_gcl_forward": (_I, [_CFG, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
+    "hd_equiv_update": (_I, [_CFG, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
+    "hd_combine_noise": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "hd_step_scalars": (_I, [_P, _P, _I, _P, _P]),
+    "hd_final_scalars": (_I, [_P, _I, _P, _P]),
+    "hd_reverse_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "hd_final_decode": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _F, _F, _F, _P, _P, _P]),
+    "hd_loop_fetch": (_I, [_P, _P, _P, _I, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises NativeError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python -m hierdiff_b200.build` "
+                "(there is no PyTorch/CPU fallback for the sampling path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.hd_abi_version() != ABI_VERSION:
+            raise NativeError(f"ABI mismatch: library {L.hd_abi_version()} vs binding {ABI_VERSION}; rebuild")
+        _lib = L
+    return _lib
+
+
+def last_error():
+    msg = lib().hd_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "native calls need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t):
+    """The product path has no CPU fallback: refuse tensors that are not on a CUDA device."""
+    if t.device.type != "cuda":
+        raise NativeError(f"tensor on {t.device}: the native sampling path needs CUDA tensors "
+                          "(there is no PyTorch/CPU fallback)")
+
+
+def engine_available(name):
+    return bool(lib().hd_engine_available(ENGINES[name]))

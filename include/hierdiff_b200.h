@@ -1,0 +1,167 @@
+/*
+ * hierdiff_b200.h - C ABI of the B200-native HierDiff coarse-grained sampling path.
+ *
+ * The drop-in boundary of this repository.  The reference (qiangbo1222/HierDiff) has no
+ * FFI of its own for this path - the path is PyTorch library calls behind a Python class
+ * surface - so each entry point below names the reference Python function whose
+ * arithmetic it replaces (paths relative to /root/reference/endiffusion).  The Python
+ * mirror in hierdiff_b200/*.py binds these through ctypes (INTEGRATION.md shows the stub
+ * a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;
+ *   - the library BORROWS all buffers, allocates nothing, never synchronises and never
+ *     throws: every call only enqueues kernels on `stream` (a cudaStream_t passed as
+ *     void*), so any sequence of calls is CUDA-graph capturable;
+ *   - int return value: 0 = ok, negative = HD_E_* (message via hd_last_error());
+ *   - tensors are fp32, row-major, in the reference's padded layout: z/eps [B,N,3+F],
+ *     h [B*N,*], x [B*N,3]; masks are given as `sizes[b]` = number of real nodes of
+ *     molecule b (node_mask[b,i] = i < sizes[b]; edge_mask[b,i,j] = i,j < sizes[b], i != j;
+ *     diffusion_qm9.py:350-359).
+ */
+#ifndef HIERDIFF_B200_H
+#define HIERDIFF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HD_API __attribute__((visibility("default")))
+#else
+#define HD_API
+#endif
+
+/* error codes */
+#define HD_OK 0
+#define HD_E_INVALID (-1)     /* bad argument / unsupported configuration */
+#define HD_E_CUDA (-2)        /* a CUDA runtime call failed */
+#define HD_E_UNSUPPORTED (-3) /* configuration valid for the reference but not built here */
+
+/* which kernels run the EGNN sub-layers */
+#define HD_ENGINE_FP32 0      /* CUDA-core fp32 FFMA kernels (reference-order arithmetic)          */
+#define HD_ENGINE_TC_STRICT 1 /* tcgen05 tensor cores, bf16x3 split operands, fp32 accumulate      */
+#define HD_ENGINE_TC_FAST 2   /* tcgen05 tensor cores, single bf16 operands, fast SiLU             */
+
+/* bits of the device-side status word (`flags`) that kernels OR into */
+#define HD_FLAG_NAN 1       /* en_dynamics.py:109-111 NaN guard fired (velocity zeroed)            */
+#define HD_FLAG_COG 2       /* models/utils.py:65-70 assert_mean_zero_with_mask(z_t) would fail    */
+#define HD_FLAG_MASK 4      /* models/utils.py:47-50,72-75 masked entries not ~0                   */
+
+typedef void* hd_stream_t; /* cudaStream_t */
+
+/* EGNN hyper-parameters: models/layers/egnn_new.py:156-190 (EGNN.__init__) as called by
+ * models/module/en_dynamics.py:17-24.  in_node_nf counts the time channel (+context). */
+typedef struct {
+  int32_t n_layers;      /* EquivariantBlocks                                   */
+  int32_t inv_sublayers; /* GCLs per block                                      */
+  int32_t hidden_nf;     /* H; this build supports H == 256                     */
+  int32_t in_node_nf;    /* features entering `embedding` (F + time + context)  */
+  int32_t attention;     /* 0/1                                                 */
+  int32_t tanh;          /* 0/1                                                 */
+  float coords_range;    /* EGNN ctor value (30); per block = / n_layers        */
+  float norm_constant;
+  float normalization_factor;
+  int32_t aggregation_mean; /* 0 = 'sum' (divide by normalization_factor), 1 = 'mean' */
+} hd_config;
+
+HD_API int32_t hd_abi_version(void);
+/* 1 when `engine` (HD_ENGINE_*) is compiled into this library, else 0 */
+HD_API int32_t hd_engine_available(int32_t engine);
+/* Kernels this library has enqueued so far in this process (host-side counter; a captured launch counts
+ * once, at capture time).  bench.py multiplies the per-step delta by the steps it replays. */
+HD_API int64_t hd_launch_count(void);
+HD_API const char* hd_last_error(void);
+
+/* Number of floats of the flat parameter buffer: the `dynamics.egnn.*` tensors of the
+ * reference state_dict concatenated in state_dict order (egnn_new.py:173-189):
+ * embedding.{weight,bias}, embedding_out.{weight,bias}, then per block b:
+ * gcl_k.{edge_mlp.0,edge_mlp.2,node_mlp.0,node_mlp.2,att_mlp.0}.{weight,bias} (k < inv_sublayers),
+ * gcl_equiv.coord_mlp.{0,2}.{weight,bias}, coord_mlp.4.weight.  nn.Linear layout [out,in]. */
+HD_API int64_t hd_weight_count(const hd_config* cfg);
+
+/* Bytes of the packed (kernel-ready) weight image and the kernel that builds it from the flat
+ * buffer: transposed fp32 copies for the FFMA engine, bf16 hi/lo operand tiles in tcgen05
+ * canonical shared-memory order for the tensor-core engines.  Replaces nothing in the
+ * reference (it keeps nn.Parameter tensors); call again after every load_state_dict. */
+HD_API int64_t hd_packed_bytes(const hd_config* cfg);
+HD_API int32_t hd_pack_weights(const hd_config* cfg, const float* w_flat, void* packed, hd_stream_t stream);
+
+/* Scratch bytes one forward needs for a padded batch of B molecules x N nodes. */
+HD_API int64_t hd_workspace_bytes(const hd_config* cfg, int32_t B, int32_t N);
+
+/* EGNN_dynamics_QM9._forward (models/module/en_dynamics.py:49-122) for mode 'egnn_dynamics',
+ * condition_time=True, context=None:  eps = [velocity | h] [B,N,3+F], F = in_node_nf-1.
+ * t is [B] (one time per molecule).  ORs HD_FLAG_NAN into *flags when the NaN guard fires. */
+HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, const float* z, const float* t,
+                            const int32_t* sizes, int32_t B, int32_t N, float* eps, void* workspace,
+                            int32_t* flags, int32_t engine, hd_stream_t stream);
+
+/* EGNN.forward (models/layers/egnn_new.py:192-205) on the canonical dense edge list of
+ * en_dynamics.py:124-143.  h_in [B*N,in_node_nf], x_in [B*N,3] -> h_out [B*N,in_node_nf], x_out. */
+HD_API int32_t hd_egnn_forward(const hd_config* cfg, const void* packed, const float* h_in, const float* x_in,
+                        const int32_t* sizes, int32_t B, int32_t N, float* h_out, float* x_out,
+                        void* workspace, int32_t engine, hd_stream_t stream);
+
+/* One GCL (egnn_new.py:35-70) = sub-layer `sub` of block `block`, in place on h [B*N,H].
+ * x [B*N,3] are the block-entry coordinates, x0 [B*N,3] the EGNN-entry coordinates
+ * (edge_attr = [|x_i-x_j|^2, |x0_i-x0_j|^2], egnn_new.py:141-144,194). */
+HD_API int32_t hd_gcl_forward(const hd_config* cfg, const void* packed, int32_t block, int32_t sub, float* h,
+                       const float* x, const float* x0, const int32_t* sizes, int32_t B, int32_t N,
+                       void* workspace, int32_t engine, hd_stream_t stream);
+
+/* EquivariantUpdate (egnn_new.py:91-110) of block `block`: x_out = (x + sum_j trans_ij/norm)*mask. */
+HD_API int32_t hd_equiv_update(const hd_config* cfg, const void* packed, int32_t block, const float* h,
+                        const float* x, const float* x0, const int32_t* sizes, int32_t B, int32_t N,
+                        float* x_out, void* workspace, int32_t engine, hd_stream_t stream);
+
+/* sample_combined_position_feature_noise (train_module/diffusion_qm9.py:445-456) given the two
+ * raw torch.randn draws: z = [CoG-free(randn_x*mask) | randn_h*mask]. */
+HD_API int32_t hd_combine_noise(const float* randn_x, const float* randn_h, const int32_t* sizes, int32_t B,
+                         int32_t N, int32_t F, float* z, hd_stream_t stream);
+
+/* Schedule scalars of one reverse step from gamma_s, gamma_t (diffusion_qm9.py:181-204,:320-334):
+ * sched[k] = {alpha_t|s, sigma2_t|s/alpha_t|s/sigma_t, sigma_t|s*sigma_s/sigma_t} for k < count. */
+HD_API int32_t hd_step_scalars(const float* gamma_s, const float* gamma_t, int32_t count, float* sched,
+                        hd_stream_t stream);
+/* Final-decode scalars from gamma_0 (diffusion_qm9.py:294-304): {alpha_0, sigma_0, exp(0.5*gamma_0)}. */
+HD_API int32_t hd_final_scalars(const float* gamma_0, int32_t count, float* sched, hd_stream_t stream);
+
+/* sample_p_zs_given_zt after the network call (diffusion_qm9.py:328-345): re-centre eps_x,
+ * mu = zt/alpha - c*eps, zs = mu + sigma*noise, re-centre zs_x.  sched is [B,3] when
+ * sched_per_mol != 0, else [3].  ORs HD_FLAG_COG / HD_FLAG_MASK when the reference's
+ * assert_mean_zero_with_mask(zt_x) would have raised. */
+HD_API int32_t hd_reverse_step(const float* zt, const float* eps, const float* randn_x, const float* randn_h,
+                        const int32_t* sizes, int32_t B, int32_t N, int32_t F, const float* sched,
+                        int32_t sched_per_mol, float* zs, int32_t* flags, hd_stream_t stream);
+
+/* sample_p_xh_given_z0 after the network call (diffusion_qm9.py:294-310, :174-179):
+ * x = ((z0 - sigma_0*eps)/alpha_0 + sigma_x*noise)[..., :3]*norm_x, h = (z0_h*norm_h + bias_h)*mask. */
+HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* randn_x, const float* randn_h,
+                        const int32_t* sizes, int32_t B, int32_t N, int32_t F, const float* sched,
+                        int32_t sched_per_mol, float norm_x, float norm_h, float bias_h, float* x,
+                        float* h, hd_stream_t stream);
+
+/* Graph-replay helpers for the T-step loop (diffusion_qm9.py:375-384).  A captured step
+ * reads its time and schedule scalars through a device-side step counter so ONE captured
+ * graph serves all T steps:  hd_loop_fetch copies t_table[*counter] into t_cur[0..B) and
+ * sched_table[*counter][0..3) into sched_cur[0..3), then increments *counter. */
+HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B,
+                      float* t_cur, float* sched_cur, hd_stream_t stream);
+
+/* Profiling hook: enqueue ONLY the fused edge kernel of sub-layer (block, sub) - sub == inv_sublayers selects
+ * the EquivariantUpdate - on the operands a previous hd_gcl_forward / hd_equiv_update call left in `workspace`
+ * (the A|B pre-projection).  Results go to workspace scratch.  Used by bench.py to time the dominant kernel
+ * alone with CUDA events; not part of the sampling path. */
+HD_API int32_t hd_edge_kernel_only(const hd_config* cfg, const void* packed, int32_t block, int32_t sub,
+                                   const float* x, const float* x0, const int32_t* sizes, int32_t B, int32_t N,
+                                   void* workspace, int32_t engine, hd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIERDIFF_B200_H */

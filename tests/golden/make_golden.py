@@ -242,13 +242,19 @@ def case_nodes_dist():
     torch.manual_seed(0)
     a = model.nodes_dist.sample(64)
     b = model.nodes_dist.sample(7)
+    hist = yaml.safe_load(open(os.path.join(REF, "conf/analyze/GEOM.yaml")))
     np.savez_compressed(os.path.join(HERE, "nodes_dist.npz"), seed0_64=np.array(a, np.int32),
-                        then_7=np.array(b, np.int32))
+                        then_7=np.array(b, np.int32), hist_keys=np.array(list(hist.keys()), np.int32),
+                        hist_counts=np.array(list(hist.values()), np.int64))
     print("nodes_dist", a[:8])
 
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:      # regenerate selected cases only, e.g. `make_golden.py nodes_dist`
+        for name in sys.argv[1:]:
+            globals()["case_" + name]()
+        sys.exit(0)
     case_forward("forward_l2", n_layers=2, sizes=[12, 7, 1, 2], N=12, seed=11)
     case_forward("forward_l1_pad", n_layers=1, sizes=[5, 9, 3], N=16, seed=12)
     case_sample("sample_c1", n_layers=6, T=50, sizes=[20, 20, 20, 20], seed=0)

@@ -1,0 +1,191 @@
+"""GPU tests of the sampler plumbing and of size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_model, random_batch, rel
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["fp32", "strict", "fast"]
+# relative tolerance of the property checks (two runs of the SAME engine on transformed inputs)
+PROP_TOL = {"fp32": 2e-5, "strict": 1e-4, "fast": 5e-2}
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def cuda(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=dev())
+
+
+@pytest.fixture(scope="module")
+def model4(tmp_path_factory):
+    return make_model(tmp_path_factory.mktemp("m4"), 4, device=dev())
+
+
+def fwd(model, z, t, sizes):
+    eps = model.dynamics.forward_sizes(cuda(t), cuda(z), cuda(sizes, torch.int32))
+    torch.cuda.synchronize()
+    return eps.cpu().numpy()
+
+
+def use(model, engine):
+    from hierdiff_b200 import native
+    if not native.engine_available(engine):
+        pytest.fail(f"engine {engine!r} is not compiled into the native library")
+    model.engine = engine
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_full_size_properties(model4, engine):
+    """C2 shape (B=64, N=40, L=4): E(3) equivariance, permutation equivariance, padding invariance, masks."""
+    use(model4, engine)
+    B, N = 64, 40
+    rng = np.random.default_rng(7)
+    sizes = rng.integers(1, N + 1, B).astype(np.int32)
+    sizes[0], sizes[1] = N, 1
+    z, t = random_batch(B, N, sizes, seed=8)
+    eps = fwd(model4, z, t, sizes)
+    tol = PROP_TOL[engine]
+    assert np.isfinite(eps).all()
+    for b in range(B):
+        assert np.all(eps[b, sizes[b]:] == 0)
+    assert np.abs(eps[..., :3].sum(1)).max() < 1e-3 * max(1.0, np.abs(eps[..., :3]).max())
+    # rotation + reflection: velocity rotates, h is invariant
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    z_rot = z.copy()
+    z_rot[..., :3] = z[..., :3] @ q.astype(np.float32)
+    eps_rot = fwd(model4, z_rot, t, sizes)
+    assert rel(eps_rot[..., :3], eps[..., :3] @ q.astype(np.float32)) < tol
+    assert rel(eps_rot[..., 3:], eps[..., 3:]) < tol
+    # permutation of the real nodes of every molecule
+    z_perm, inv = z.copy(), []
+    for b in range(B):
+        p = rng.permutation(sizes[b])
+        z_perm[b, :sizes[b]] = z[b, p]
+        inv.append(p)
+    eps_perm = fwd(model4, z_perm, t, sizes)
+    want = eps.copy()
+    for b in range(B):
+        want[b, :sizes[b]] = eps[b, inv[b]]
+    assert rel(eps_perm, want) < tol
+    # padding invariance: the same molecules in a wider padded batch (N=56)
+    z_pad = np.zeros((B, 56, z.shape[2]), np.float32)
+    z_pad[:, :N] = z
+    eps_pad = fwd(model4, z_pad, t, sizes)
+    assert rel(eps_pad[:, :N], eps) < tol
+    assert np.all(eps_pad[:, N:] == 0)
+
+
+@pytest.mark.parametrize("engine", ["strict", "fast"])
+def test_tensor_core_engines_track_fp32_engine_at_full_size(model4, engine):
+    """B=64, N=40, L=4 (too big for the CPU oracle in a test): tensor-core engines vs the fp32 FFMA engine."""
+    B, N = 64, 40
+    sizes = np.full(B, N, np.int32)
+    sizes[::7] = 23
+    z, t = random_batch(B, N, sizes, seed=21)
+    use(model4, "fp32")
+    ref = fwd(model4, z, t, sizes)
+    use(model4, engine)
+    got = fwd(model4, z, t, sizes)
+    assert rel(got, ref) < (5e-5 if engine == "strict" else 3e-2)
+
+
+def test_graph_replay_draws_the_same_noise_as_eager():
+    """torch's graph-safe Philox: normal_ captured in a CUDA graph == the eager draws for the same seed."""
+    a = torch.empty(64, 40, 3, device=dev())
+    b = torch.empty(64, 40, 8, device=dev())
+    torch.manual_seed(123)
+    eager = []
+    for _ in range(4):
+        eager.append((a.normal_().clone(), b.normal_().clone()))
+    torch.manual_seed(123)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    rng = torch.cuda.get_rng_state(dev())
+    with torch.cuda.stream(s):
+        a.normal_()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        a.normal_()
+        b.normal_()
+    torch.cuda.synchronize()
+    torch.cuda.set_rng_state(rng, dev())
+    for k in range(4):
+        g.replay()
+        assert torch.equal(a, eager[k][0]) and torch.equal(b, eager[k][1]), k
+
+
+@pytest.mark.parametrize("engine", ["fp32", "strict"])
+def test_graph_loop_equals_eager_loop(tmp_path, engine):
+    """The captured T-step loop is bit-identical to issuing the same kernels eagerly (same seed)."""
+    outs = []
+    for use_graph in (True, False):
+        model = make_model(tmp_path, 1, timesteps=24, device=dev(), engine="fp32")
+        use(model, engine)
+        model.use_cuda_graph = use_graph
+        model.steps_per_graph = 8
+        torch.manual_seed(5)
+        outs.append(model.sample_padded([9, 4, 12, 12, 1], dev()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.isfinite(outs[0][0]).all()
+
+
+def test_sample_api_layout_and_determinism(tmp_path):
+    """diffusion_qm9.py:347-395,:397-436: result layout, sizes from nodes_dist, determinism under a seed."""
+    model = make_model(tmp_path, 1, timesteps=12, device=dev(), engine="fp32")
+    torch.manual_seed(0)
+    res, names = model.sample_batches(batch_size=6, num_batches=2, device=dev())
+    assert names == [] and len(res) == 12
+    torch.manual_seed(0)
+    sizes = model.nodes_dist.sample(6)
+    for r, n in zip(res[:6], sizes):
+        assert set(r) == {"x", "h"}
+        assert r["x"].shape == (n, 3) and r["h"].shape == (n, 8)
+        assert r["x"].device.type == "cpu" and r["x"].dtype == torch.float32
+    torch.manual_seed(0)
+    res2, _ = model.sample_batches(batch_size=6, num_batches=2, device=dev())
+    for a, b in zip(res, res2):
+        assert torch.equal(a["x"], b["x"]) and torch.equal(a["h"], b["h"])
+    import pickle
+    blob = pickle.loads(pickle.dumps((res, names)))     # the tuple sampler.py:40-41 writes
+    assert torch.equal(blob[0][3]["h"], res[3]["h"])
+
+
+def test_eager_step_api_matches_loop(tmp_path):
+    """sample_p_zs_given_zt / sample_p_xh_given_z0 with the reference's argument lists reproduce the loop."""
+    from hierdiff_b200.utils import masks_from_sizes
+    model = make_model(tmp_path, 1, timesteps=6, device=dev(), engine="fp32")
+    sizes = [7, 3, 7]
+    B, N, T = 3, 7, 6
+    torch.manual_seed(11)
+    x_loop, h_loop = model.sample_padded(sizes, dev())
+    torch.manual_seed(11)
+    nm, em = masks_from_sizes(sizes, N, dev())
+    z = model.sample_combined_position_feature_noise(B, N, nm)
+    for s in reversed(range(T)):
+        s_arr = torch.full((B, 1), s, device=dev()) / T
+        t_arr = (torch.full((B, 1), s, device=dev()) + 1) / T
+        z = model.sample_p_zs_given_zt(s_arr, t_arr, z, nm, em, None, mol_shape=N)
+    x, h = model.sample_p_xh_given_z0(z, nm, em, None)
+    assert rel(x.cpu().numpy(), x_loop.numpy()) < 1e-5
+    assert rel(h.cpu().numpy(), h_loop.numpy()) < 1e-5
+
+
+def test_flags_report_violations(tmp_path):
+    """Device-side status word: a non-centred z_t trips the reference's assert_mean_zero_with_mask."""
+    from hierdiff_b200.utils import masks_from_sizes
+    model = make_model(tmp_path, 1, timesteps=6, device=dev(), engine="fp32")
+    nm, em = masks_from_sizes([5, 5], 5, dev())
+    z = torch.randn(2, 5, 11, device=dev())
+    z[..., :3] += 3.0
+    s = torch.full((2, 1), 0.5, device=dev())
+    with pytest.raises(AssertionError):
+        model.sample_p_zs_given_zt(s, s + 0.1, z, nm, em, None)
+    z = torch.full((2, 5, 11), float("nan"), device=dev())
+    eps = model.phi(z, s, nm, em, None)
+    assert model.dynamics.nan_guard_fired()
+    assert torch.all(eps[..., :3] == 0)

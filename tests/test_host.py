@@ -1,0 +1,148 @@
+"""CPU tests of the host-side mirror: configuration, masks, schedule modules, library surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, histogram_file, make_model
+from oracle import hd_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports exactly what include/hierdiff_b200.h declares."""
+    from hierdiff_b200 import build, native
+    build.build()
+    header = open(os.path.join(ROOT, "include", "hierdiff_b200.h")).read()
+    declared = set(re.findall(r"HD_API\s+[\w\s\*]+?\b(hd_\w+)\s*\(", header))
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    L = ctypes.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert native.lib().hd_abi_version() == native.ABI_VERSION
+
+
+def test_layout_sizes_match_reference_parameter_count():
+    from hierdiff_b200 import native
+    for n_layers, expect in [(4, 3959574), (6, 5935386)]:    # SURVEY.md 8b [probe]: whole model
+        cfg = native.HdConfig(n_layers, 2, 256, 9, 1, 1, 30.0, 0.0, 10.0, 0)
+        n = native.lib().hd_weight_count(cfg)
+        assert n == O.lib().hdo_weight_count(ctypes.byref(O.make_config(n_layers)))
+        assert n + 3077 == expect         # + the gamma network's 3077 parameters
+        assert native.lib().hd_packed_bytes(cfg) > 4 * n
+    bad = native.HdConfig(4, 2, 128, 9, 1, 1, 30.0, 0.0, 10.0, 0)
+    assert native.lib().hd_weight_count(bad) < 0 and "hidden_nf" in native.last_error()
+
+
+def test_state_dict_keys_and_shapes_equal_reference(tmp_path):
+    model = make_model(tmp_path, n_layers=2)
+    sd = model.state_dict()
+    cfg = O.make_config(2)
+    ref = dict(O.egnn_shapes(cfg))
+    ref.update({"buffer": (1,), "gamma.gamma_0": (1,), "gamma.gamma_1": (1,), "gamma.l1.weight": (1, 1),
+                "gamma.l1.bias": (1,), "gamma.l2.weight": (1024, 1), "gamma.l2.bias": (1024,),
+                "gamma.l3.weight": (1, 1024), "gamma.l3.bias": (1,)})
+    assert {k: tuple(v.shape) for k, v in sd.items()} == ref
+    # flat parameter order of the EGNN == order of the native flat buffer
+    names = ["dynamics.egnn." + n for n, _ in model.dynamics.egnn.named_parameters()]
+    assert names == O.egnn_key_order(cfg)
+
+
+def test_gamma_network_matches_reference_fixture(tmp_path):
+    g = np.load(os.path.join(GOLDEN, "gamma.npz"))
+    model = make_model(tmp_path, n_layers=1)
+    with torch.no_grad():
+        got = model.gamma(torch.from_numpy(g["t"]).view(-1, 1))[:, 0].numpy()
+    assert np.abs(got - g["gamma_batched"]).max() < 1e-5
+    model2 = make_model(tmp_path, n_layers=1, noise_schedule="polynomial_2")
+    assert np.array_equal(model2.gamma.gamma.numpy(), g["gamma_poly2_table"])
+    with torch.no_grad():
+        got2 = model2.gamma(torch.from_numpy(g["t"]).view(-1, 1))[:, 0].numpy()
+    assert np.array_equal(got2, g["gamma_poly2"])
+
+
+def test_nodes_dist_reproduces_reference_draws(tmp_path):
+    g = np.load(os.path.join(GOLDEN, "nodes_dist.npz"))
+    model = make_model(tmp_path, n_layers=1)
+    torch.manual_seed(0)
+    assert model.nodes_dist.sample(64) == g["seed0_64"].tolist()
+    assert model.nodes_dist.sample(7) == g["then_7"].tolist()
+
+
+def test_masks_roundtrip_and_rejection():
+    from hierdiff_b200.utils import check_edge_index, check_edge_mask, masks_from_sizes, sizes_from_node_mask
+    sizes = [3, 5, 1]
+    nm, em = masks_from_sizes(sizes, 5, "cpu")
+    assert nm.shape == (3, 5, 1) and em.shape == (3, 5, 5)
+    assert sizes_from_node_mask(nm, 3, 5).tolist() == sizes
+    check_edge_mask(em, torch.tensor(sizes), 3, 5)
+    assert int(em[1].sum()) == 20 and not em[0, 3:].any() and not em[0, :, 3:].any()
+    bad = nm.clone()
+    bad[0, 0] = False
+    with pytest.raises(NotImplementedError):
+        sizes_from_node_mask(bad, 3, 5)
+    em2 = em.clone()
+    em2[1, 0, 0] = True
+    with pytest.raises(NotImplementedError):
+        check_edge_mask(em2, torch.tensor(sizes), 3, 5)
+    from hierdiff_b200 import EGNN_dynamics_QM9
+    dyn = EGNN_dynamics_QM9(in_node_nf=9, context_node_nf=0, n_dims=3, hidden_nf=256)
+    rows, cols = dyn.get_adj_matrix(4, 2)
+    assert rows[:5].tolist() == [0, 0, 0, 0, 1] and cols[:5].tolist() == [0, 1, 2, 3, 0] and rows[16] == 4
+    check_edge_index((rows, cols), 2, 4)
+    with pytest.raises(NotImplementedError):
+        check_edge_index((cols, rows), 2, 4)
+
+
+def test_config_composition(tmp_path):
+    from hierdiff_b200.config import instantiate, load_config
+    conf = tmp_path / "conf"
+    (conf / "model").mkdir(parents=True)
+    (conf / "sample").mkdir()
+    hist = histogram_file(tmp_path)
+    (conf / "sample.yaml").write_text(
+        "defaults:\n  - model: tiny\n  - sample: default\n  - override hydra/job_logging: colorlog\n"
+        "checkpoint: /nowhere/diffusion.ckpt\nhydra:\n  run:\n    dir: x/${now:%Y}\n")
+    (conf / "sample" / "default.yaml").write_text("batch_size: 2\nnum_batches: 16\n")
+    from hierdiff_b200.config import default_model_cfg
+    import yaml
+    node = {"_target_": "train_module.diffusion_qm9.DiffusionQM9",
+            "cfg": dict(default_model_cfg(n_layers=1, analyze=hist))}
+    node["cfg"]["dynamics"] = dict(node["cfg"]["dynamics"])
+    node["cfg"]["pre_noise"] = dict(node["cfg"]["pre_noise"])
+    (conf / "model" / "tiny.yaml").write_text(yaml.safe_dump(node))
+    cfg = load_config(str(conf), "sample", ["sample.batch_size=5", "model.cfg.timesteps=50"])
+    assert cfg.sample.batch_size == 5 and cfg.sample.num_batches == 16
+    assert cfg.checkpoint == "/nowhere/diffusion.ckpt" and "hydra" not in cfg
+    model = instantiate(cfg.model, cfg=cfg, _recursive_=False)
+    assert model.T == 50 and model.dynamics.egnn.n_layers == 1
+    assert model.cfg.sample.batch_size == 5            # root keys are visible on the model cfg, as with hydra
+    assert model.cfg.dynamics.in_node_nf == 9          # mutated like the reference (diffusion_qm9.py:47,90)
+    with pytest.raises(NotImplementedError):
+        instantiate({"_target_": "somewhere.Else"}, cfg=cfg)
+
+
+def test_product_path_fails_loudly_without_cuda(tmp_path):
+    """No CPU fallback: sampling on a CPU device raises instead of silently running PyTorch."""
+    from hierdiff_b200 import native
+    model = make_model(tmp_path, n_layers=1, timesteps=5)
+    with pytest.raises(native.NativeError):
+        model.sample(2, torch.device("cpu"))
+    nm = torch.ones(1, 4, 1, dtype=torch.bool)
+    em = ~torch.eye(4, dtype=torch.bool).unsqueeze(0)
+    with pytest.raises(native.NativeError):
+        model.phi(torch.zeros(1, 4, 11), torch.zeros(1, 1), nm, em, None)
+
+
+def test_unsupported_options_raise(tmp_path):
+    from hierdiff_b200 import EGNN, EGNN_dynamics_QM9
+    with pytest.raises(NotImplementedError):
+        EGNN(9, 1, 256, sin_embedding=True)
+    with pytest.raises(NotImplementedError):
+        EGNN_dynamics_QM9(9, 0, 3, mode="gnn_dynamics")
+    with pytest.raises(NotImplementedError):
+        EGNN_dynamics_QM9(9, 2, 3)
