@@ -93,6 +93,7 @@ struct Workspace {
   int64_t hout;   // [BN][Fi]
   int64_t eps_raw;// [BN][3+F]
   int64_t nanflag;// [1] int32 per forward
+  int64_t row_off;// [B+1] int32: prefix of n_b * pad8(n_b) (edge rows per molecule, tensor-core engines)
   int64_t total_bytes;
 };
 Workspace make_workspace(const hd_config& cfg, int B, int N);
@@ -122,6 +123,7 @@ struct FwdCtx {
   const int32_t* sizes;
   int B, N;
   cudaStream_t stream;
+  mutable bool planned = false;  // ws.row_off holds the edge-row prefix for `sizes`
 };
 
 // GCL sub-layer `si` (index into L.subs) in place on ctx.ws h; reads x (ws.x) and x0.

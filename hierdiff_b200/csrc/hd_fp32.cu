@@ -221,4 +221,9 @@ int fp32_edge_only(const FwdCtx& c, int si, const float* x, const float* x0) {
   return HD_OK;
 }
 
+int linear_fp32(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const float* WT,
+                int n_out, const float* bias, float* Y, int ldy, int mode, const float* resid) {
+  return linear(c, X1, ld1, K1, X2, ld2, K2, WT, n_out, bias, Y, ldy, mode, resid);
+}
+
 }  // namespace hd

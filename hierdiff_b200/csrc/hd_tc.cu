@@ -1,17 +1,632 @@
-// hd_tc.cu - tensor-core engines (placeholder until the tcgen05 kernels land)
+// hd_tc.cu - tensor-core engines (HD_ENGINE_TC_STRICT / HD_ENGINE_TC_FAST): the fused edge kernel.
+//
+// One persistent, warp-specialised kernel per edge-MLP sub-layer (GCL or EquivariantUpdate):
+//
+//   rows     : the real (i,j) node pairs of every molecule, j padded to a multiple of 8 per receiver i;
+//              every CTA owns a contiguous range of whole receivers (no cross-CTA reduction, no atomics)
+//   producer : 4 warps build the MMA A operand on the fly, m1_ij = SiLU(A_i + B_j + r_ij*wr + d0_ij*wd)
+//              (layer 1 of the edge MLP split per node), as bf16 (hi [+ lo]) core matrices in a
+//              shared-memory ring, K = 32 per stage
+//   MMA      : 1 thread issues tcgen05.mma (kind::f16, M=128 per CTA, N=256, K=16) against W2 resident in
+//              shared memory; strict mode runs 3 passes (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM
+//              accumulator; cta_group::2 pairs two SMs so each holds one 128-row half of W2 (hi+lo = 128 KB)
+//   epilogue : 4 warps read the accumulator from TMEM (thread = edge row): + b2, SiLU, attention / coord
+//              dot product, mask, then a shuffle transpose-reduction over the 8 rows of a group and a
+//              per-receiver running sum -> agg_i (GCL) or x_i + sum_j trans_ij (EquivariantUpdate)
+//
+// Accumulators are double buffered in TMEM (2 x 256 columns), so tile t's epilogue overlaps tile t+1's MMAs
+// and tile t+2's operand generation.
+#include <cuda_bf16.h>
+
 #include "hd_common.cuh"
+#include "hd_ptx.cuh"
+
 namespace hd {
-bool tc_available() { return false; }
-int tc_gcl(const FwdCtx&, int, float*, const float*, const float*, int) {
-  set_error("tensor-core engine not built");
-  return HD_E_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int TILE_M = 128;           // edge rows per CTA tile
+constexpr int KCH = 32;               // K columns per operand stage
+constexpr int NCH = H / KCH;          // 8 stages per tile
+constexpr int NSTAGE = 4;             // operand ring depth
+constexpr int A_KG = 2048;            // bytes between K-adjacent core matrices of A (128 rows x 16 B)
+constexpr int A_HALF = 4 * A_KG;      // one stage of hi (or lo): 4 core-matrix columns = 8 KB
+constexpr int W_KG = 2048;            // bytes between K-adjacent core matrices of a 128-row W half image
+constexpr int W_HALF = (H / 8) * W_KG;  // 64 KB: one 128-row half image (hi or lo)
+constexpr int META_BUFS = 3;
+constexpr int GRP_BUFS = 4;           // per-tile group table ring (receiver of each 8-row group)
+constexpr int MAX_B = 511;            // molecules per launch (row_off table in shared memory)
+constexpr int NTHREADS = 288;         // 4 producer + 4 epilogue + 1 MMA/alloc warp
+
+struct RowMeta {      // 32 bytes per edge row of a tile
+  float r, d0;        // |x_i-x_j|^2, |x0_i-x0_j|^2
+  int recv, send;     // flat node rows b*N+i, b*N+j
+  float cd0, cd1, cd2;  // (x_i-x_j)/(sqrt(r+1e-8)+norm_constant)  (EquivariantUpdate only)
+  int flags;          // bit0: row is a real edge slot (j<n, inside this CTA's range); bit1: j==i
+};
+
+struct Params {
+  const float* ab;     // [BN][2H]  A_i (+b1) | B_j
+  const float* x;      // [BN][3] block-entry coordinates
+  const float* x0;     // [BN][3] EGNN-entry coordinates
+  const int32_t* sizes;
+  const int32_t* row_off;  // [B+1] prefix of n_b * pad8(n_b)
+  const void* w_hi;    // bf16 images [2][32][128][8]
+  const void* w_lo;
+  const float *b2, *wa, *ba, *wr, *wd;
+  float* out;          // GCL: agg [BN][H]; EQUIV: x_out [BN][3]
+  int B, N;
+  int attention, use_tanh;
+  float range, norm_constant, norm_div;
+};
+
+template <bool STRICT, int CG>
+struct Smem {
+  static constexpr int W_BYTES = (CG == 2 ? 1 : 2) * W_HALF * (STRICT ? 2 : 1);
+  static constexpr int STAGE = A_HALF * (STRICT ? 2 : 1);
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = OFF_W + W_BYTES;
+  static constexpr int OFF_SCR = OFF_A + NSTAGE * STAGE;           // [16][H] fp32
+  static constexpr int OFF_VEC = OFF_SCR + 16 * H * 4;             // b2, wa, wr, wd
+  static constexpr int OFF_ROW = OFF_VEC + 4 * H * 4;              // row_off [MAX_B+1]
+  static constexpr int OFF_META = OFF_ROW + (MAX_B + 1) * 4;
+  static constexpr int OFF_GRP = OFF_META + META_BUFS * TILE_M * (int)sizeof(RowMeta);   // int2 [GRP_BUFS][16]
+  static constexpr int OFF_BAR = OFF_GRP + GRP_BUFS * 16 * 8;
+  // barriers: full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2], w_local, w_ready ; then tmem ptr
+  static constexpr int NBAR = 2 * NSTAGE + 6;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int TOTAL = OFF_TMEM + 16;
+};
+
+// largest b with row_off[b] <= R  (row_off[0] = 0, row_off[B] = total > R)
+__device__ __forceinline__ int find_mol(const int* row_off, int B, int R) {
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (row_off[mid] <= R) lo = mid; else hi = mid;
+  }
+  return lo;
 }
-int tc_equiv(const FwdCtx&, int, const float*, const float*, const float*, float*, int) {
-  set_error("tensor-core engine not built");
-  return HD_E_UNSUPPORTED;
+// first receiver boundary >= S
+__device__ __forceinline__ int align_recv(const int* row_off, const int32_t* sizes, int B, int S) {
+  const int total = row_off[B];
+  if (S >= total) return total;
+  const int b = find_mol(row_off, B, S);
+  const int n = sizes[b], npad = (n + 7) & ~7;
+  const int local = S - row_off[b];
+  return row_off[b] + ((local + npad - 1) / npad) * npad;
 }
-int tc_edge_only(const FwdCtx&, int, const float*, const float*, int) {
-  set_error("tensor-core engine not built");
-  return HD_E_UNSUPPORTED;
+
+template <bool STRICT>
+__device__ __forceinline__ float silu_edge(float v) {
+  if constexpr (STRICT) {
+    // v * 1/(1+exp(-v)) with ex2.approx / rcp.approx (each ~1-2 ulp)
+    const float e = ptx::ex2_approx(-1.4426950408889634f * v);
+    return v * ptx::rcp_approx(1.0f + e);
+  } else {
+    const float hv = 0.5f * v;
+    return fmaf(hv, ptx::tanh_approx(hv), hv);
+  }
 }
+
+template <bool GCL, bool STRICT, int CG>
+__global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
+  using S = Smem<STRICT, CG>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0;
+
+  float* s_scr = reinterpret_cast<float*>(smem + S::OFF_SCR);
+  float* s_b2 = reinterpret_cast<float*>(smem + S::OFF_VEC);
+  float* s_wa = s_b2 + H;
+  float* s_wr = s_wa + H;
+  float* s_wd = s_wr + H;
+  int* s_row = reinterpret_cast<int*>(smem + S::OFF_ROW);
+  RowMeta* s_meta = reinterpret_cast<RowMeta*>(smem + S::OFF_META);
+  int2* s_grp = reinterpret_cast<int2*>(smem + S::OFF_GRP);   // {receiver row, group is inside this CTA's range}
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
+  const uint32_t bar0 = sbase + S::OFF_BAR;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto bar_accf = [&](int a) { return bar0 + 8u * (2 * NSTAGE + a); };
+  auto bar_acce = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
+  const uint32_t bar_wl = bar0 + 8u * (2 * NSTAGE + 4), bar_wr = bar0 + 8u * (2 * NSTAGE + 5);
+
+  // ---- one-time setup --------------------------------------------------------------------------
+  for (int k = tid; k < H; k += NTHREADS) {
+    s_b2[k] = p.b2[k];
+    s_wa[k] = p.wa[k];
+    s_wr[k] = p.wr[k];
+    s_wd[k] = p.wd[k];
+  }
+  for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      ptx::mbar_init(bar_full(s), 4 * CG);   // one elected arrive per producer warp of each CTA
+      ptx::mbar_init(bar_empty(s), 1);       // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(bar_accf(a), 1);        // tcgen05.commit
+      ptx::mbar_init(bar_acce(a), 4 * CG);   // one elected arrive per epilogue warp of each CTA
+    }
+    ptx::mbar_init(bar_wl, 1);
+    ptx::mbar_init(bar_wr, CG);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  // ---- this CTA's rows ---------------------------------------------------------------------------
+  const int nCTA = gridDim.x;
+  const int total = s_row[p.B];
+  const int rpc = (total + nCTA - 1) / nCTA;
+  auto range_of = [&](int c, int& a, int& e) {
+    a = align_recv(s_row, p.sizes, p.B, min(c * rpc, total));
+    e = align_recv(s_row, p.sizes, p.B, min((c + 1) * rpc, total));
+  };
+  int row_begin, row_end;
+  range_of(blockIdx.x, row_begin, row_end);
+  int ntiles = (row_end - row_begin + TILE_M - 1) / TILE_M;
+  if constexpr (CG == 2) {
+    int pa, pe;
+    range_of(blockIdx.x ^ 1, pa, pe);
+    ntiles = max(ntiles, (pe - pa + TILE_M - 1) / TILE_M);
+  }
+
+  if (warp < 4) {
+    // =========================== producers ===========================
+    const int rsub = (lane >> 1) & 7;                 // row within an 8-row group
+    const int qsub = 2 * (lane >> 4) + (lane & 1);    // 16-byte quad within a 16-column half stage
+    for (int t = 0; t < ntiles; ++t) {
+      RowMeta* meta = s_meta + (t % META_BUFS) * TILE_M;
+      {  // row metadata of tile row `tid`
+        const int R = row_begin + t * TILE_M + tid;
+        RowMeta m;
+        m.r = m.d0 = m.cd0 = m.cd1 = m.cd2 = 0.f;
+        m.recv = m.send = 0;
+        m.flags = 0;
+        if (R < row_end) {
+          const int b = find_mol(s_row, p.B, R);
+          const int n = p.sizes[b], npad = (n + 7) & ~7;
+          const int local = R - s_row[b];
+          const int i = local / npad, j = local - i * npad;
+          m.recv = b * p.N + i;
+          m.send = m.recv;
+          if (j < n) {
+            m.send = b * p.N + j;
+            m.flags = 1 | (j == i ? 2 : 0);
+            const float* xi = p.x + 3 * (int64_t)m.recv;
+            const float* xj = p.x + 3 * (int64_t)m.send;
+            const float* oi = p.x0 + 3 * (int64_t)m.recv;
+            const float* oj = p.x0 + 3 * (int64_t)m.send;
+            const float d0 = xi[0] - xj[0], d1 = xi[1] - xj[1], d2 = xi[2] - xj[2];
+            const float e0 = oi[0] - oj[0], e1 = oi[1] - oj[1], e2 = oi[2] - oj[2];
+            m.r = d0 * d0 + d1 * d1 + d2 * d2;
+            m.d0 = e0 * e0 + e1 * e1 + e2 * e2;
+            if (!GCL) {
+              const float nrm = sqrtf(m.r + 1e-8f) + p.norm_constant;
+              m.cd0 = d0 / nrm;
+              m.cd1 = d1 / nrm;
+              m.cd2 = d2 / nrm;
+            }
+          } else {
+            m.flags = 4;  // padding slot inside a real receiver's group
+          }
+        }
+        meta[tid] = m;
+        if ((tid & 7) == 0) s_grp[(t % GRP_BUFS) * 16 + (tid >> 3)] = make_int2(m.recv, m.flags != 0);
+      }
+      ptx::named_bar_sync(1, 128);
+      // the 4 rows this thread feeds: 32*warp + 8*rb + rsub
+      float rr[4], dd[4];
+      const float* pa[4];
+      const float* pb[4];
+      bool ok[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) {
+        const RowMeta& m = meta[32 * warp + 8 * rb + rsub];
+        rr[rb] = m.r;
+        dd[rb] = m.d0;
+        ok[rb] = (m.flags & 1) != 0;
+        pa[rb] = p.ab + (int64_t)m.recv * (2 * H) + 4 * qsub;
+        pb[rb] = p.ab + (int64_t)m.send * (2 * H) + H + 4 * qsub;
+      }
+      // software pipeline over half stages (16 K-columns): the loads of the next half stage are in flight
+      // while the current one is computed
+      float4 va0[4], vb0[4], va1[4], vb1[4];
+      auto load_half = [&](float4 (&va)[4], float4 (&vb)[4], int hs) {
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+          va[rb] = __ldg(reinterpret_cast<const float4*>(pa[rb] + 16 * hs));
+          vb[rb] = __ldg(reinterpret_cast<const float4*>(pb[rb] + 16 * hs));
+        }
+      };
+      auto half_step = [&](const float4 (&va)[4], const float4 (&vb)[4], int c, int ph, int s) {
+        const int k0 = 32 * c + 16 * ph + 4 * qsub;
+        const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
+        const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
+        uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8;
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+          const float4 a = va[rb], b = vb[rb];
+          float v0 = fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x));
+          float v1 = fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y));
+          float v2 = fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z));
+          float v3 = fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w));
+          v0 = ok[rb] ? silu_edge<STRICT>(v0) : 0.f;
+          v1 = ok[rb] ? silu_edge<STRICT>(v1) : 0.f;
+          v2 = ok[rb] ? silu_edge<STRICT>(v2) : 0.f;
+          v3 = ok[rb] ? silu_edge<STRICT>(v3) : 0.f;
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+          uint2 hi;
+          hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+          hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+          uint8_t* dst = stage + (32 * warp + 8 * rb + rsub) * 16;
+          *reinterpret_cast<uint2*>(dst) = hi;
+          if constexpr (STRICT) {
+            const float l0 = v0 - __uint_as_float(hi.x << 16), l1 = v1 - __uint_as_float(hi.x & 0xffff0000u);
+            const float l2 = v2 - __uint_as_float(hi.y << 16), l3 = v3 - __uint_as_float(hi.y & 0xffff0000u);
+            const __nv_bfloat162 g01 = __floats2bfloat162_rn(l0, l1), g23 = __floats2bfloat162_rn(l2, l3);
+            uint2 lo;
+            lo.x = *reinterpret_cast<const uint32_t*>(&g01);
+            lo.y = *reinterpret_cast<const uint32_t*>(&g23);
+            *reinterpret_cast<uint2*>(dst + A_HALF) = lo;
+          }
+        }
+      };
+      load_half(va0, vb0, 0);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int gc = t * NCH + c, s = gc % NSTAGE;
+        load_half(va1, vb1, 2 * c + 1);
+        ptx::mbar_wait(bar_empty(s), ((gc / NSTAGE) & 1) ^ 1);
+        half_step(va0, vb0, c, 0, s);
+        if (c + 1 < NCH) load_half(va0, vb0, 2 * c + 2);
+        half_step(va1, vb1, c, 1, s);
+        ptx::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_full(s), 0);
+          else ptx::mbar_arrive(bar_full(s));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // =========================== epilogue ===========================
+    const int q = warp - 4, etid = tid - 128;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
+    float carry0 = 0.f, carry1 = 0.f;
+    int cur_recv = -1;
+    const float ba = GCL ? p.ba[0] : 0.f;
+    auto flush = [&]() {
+      if (cur_recv < 0) return;
+      if (GCL) {
+        float2 o;
+        o.x = carry0 / p.norm_div;
+        o.y = carry1 / p.norm_div;
+        *reinterpret_cast<float2*>(p.out + (int64_t)cur_recv * H + 2 * etid) = o;
+      } else if (etid < 3) {
+        p.out[(int64_t)cur_recv * 3 + etid] = p.x[(int64_t)cur_recv * 3 + etid] + carry0 / p.norm_div;
+      }
+    };
+    for (int t = 0; t < ntiles; ++t) {
+      const int as = t & 1;
+      const RowMeta* meta = s_meta + (t % META_BUFS) * TILE_M;
+      ptx::mbar_wait(bar_accf(as), (t >> 1) & 1);
+      ptx::tc_fence_after();
+      const RowMeta mine = meta[32 * q + lane];
+      const bool live = (mine.flags & 3) == 1;   // real, off-diagonal edge
+      const uint32_t acc = lane_base + 256u * as;
+      float v[32];
+      float dot = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        ptx::tmem_ld32(acc + 32 * cc, v);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_b2 + 32 * cc + 4 * k4);
+          const float4 ww = *reinterpret_cast<const float4*>(s_wa + 32 * cc + 4 * k4);
+          const float m0 = silu_edge<STRICT>(v[4 * k4 + 0] + bb.x), m1 = silu_edge<STRICT>(v[4 * k4 + 1] + bb.y);
+          const float m2 = silu_edge<STRICT>(v[4 * k4 + 2] + bb.z), m3 = silu_edge<STRICT>(v[4 * k4 + 3] + bb.w);
+          dot = fmaf(m0, ww.x, dot);
+          dot = fmaf(m1, ww.y, dot);
+          dot = fmaf(m2, ww.z, dot);
+          dot = fmaf(m3, ww.w, dot);
+          v[4 * k4 + 0] = m0; v[4 * k4 + 1] = m1; v[4 * k4 + 2] = m2; v[4 * k4 + 3] = m3;
+        }
+        if (GCL) ptx::tmem_st32(acc + 32 * cc, v);
+      }
+      if (GCL) {
+        ptx::tmem_wait_st();
+        float att = 1.0f;
+        if (p.attention) att = STRICT ? 1.0f / (1.0f + __expf(-(dot + ba))) : fmaf(0.5f, ptx::tanh_approx(0.5f * (dot + ba)), 0.5f);
+        const float scale = live ? att : 0.f;
+        if (t > 0) ptx::named_bar_sync(2, 128);   // previous tile's combine has finished reading the scratch
+        const int c4 = (lane & 4) ? 16 : 0, c2 = (lane & 2) ? 8 : 0, c1 = (lane & 1) ? 4 : 0;
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          ptx::tmem_ld32(acc + 32 * cc, v);
+          ptx::tmem_wait_ld();
+          float f[16], g[8], hsum[4];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float lo_v = v[k] * scale, hi_v = v[k + 16] * scale;
+            const float send = (lane & 4) ? lo_v : hi_v;
+            const float keep = (lane & 4) ? hi_v : lo_v;
+            f[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float send = (lane & 2) ? f[k] : f[k + 8];
+            const float keep = (lane & 2) ? f[k + 8] : f[k];
+            g[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float send = (lane & 1) ? g[k] : g[k + 4];
+            const float keep = (lane & 1) ? g[k + 4] : g[k];
+            hsum[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          float4 o;
+          o.x = hsum[0]; o.y = hsum[1]; o.z = hsum[2]; o.w = hsum[3];
+          *reinterpret_cast<float4*>(s_scr + (4 * q + (lane >> 3)) * H + 32 * cc + c4 + c2 + c1) = o;
+        }
+      } else {
+        float tv = p.use_tanh ? (STRICT ? tanhf(dot) : ptx::tanh_approx(dot)) * p.range : dot;
+        if (!live) tv = 0.f;
+        float t0 = mine.cd0 * tv, t1 = mine.cd1 * tv, t2 = mine.cd2 * tv;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+          t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+          t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        }
+        if (t > 0) ptx::named_bar_sync(2, 128);
+        if ((lane & 7) == 0) {
+          float* dst = s_scr + (4 * q + (lane >> 3)) * H;
+          dst[0] = t0; dst[1] = t1; dst[2] = t2;
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_acce(as), 0);
+        else ptx::mbar_arrive(bar_acce(as));
+      }
+      ptx::named_bar_sync(3, 128);   // scratch complete
+      // per-receiver running sums: groups of a tile are ordered by receiver
+      if (GCL || etid < 3) {
+#pragma unroll 1
+        for (int g = 0; g < 16; ++g) {
+          const int2 gi = s_grp[(t % GRP_BUFS) * 16 + g];
+          if (!gi.y) continue;                    // group outside this CTA's range
+          if (gi.x != cur_recv) {
+            flush();
+            cur_recv = gi.x;
+            carry0 = carry1 = 0.f;
+          }
+          if (GCL) {
+            const float2 s2 = *reinterpret_cast<const float2*>(s_scr + g * H + 2 * etid);
+            carry0 += s2.x;
+            carry1 += s2.y;
+          } else {
+            carry0 += s_scr[g * H + etid];
+          }
+        }
+      }
+    }
+    flush();
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      // resident W2 image(s): this CTA's 128-row half (CG=2) or both halves (CG=1)
+      const uint32_t wbytes = S::W_BYTES;
+      ptx::mbar_expect_tx(bar_wl, wbytes);
+      const int nhalf = CG == 2 ? 1 : 2;
+      for (int hf = 0; hf < nhalf; ++hf) {
+        const int src_half = CG == 2 ? (int)rank : hf;
+        for (int part = 0; part < (STRICT ? 2 : 1); ++part) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(part ? p.w_lo : p.w_hi) + (size_t)src_half * W_HALF;
+          const uint32_t dst = sbase + S::OFF_W + (hf * (STRICT ? 2 : 1) + part) * W_HALF;
+          for (int off = 0; off < W_HALF; off += 16384) ptx::bulk_g2s(dst + off, src + off, 16384, bar_wl);
+        }
+      }
+      ptx::mbar_wait(bar_wl, 0);
+      if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_wr, 0);
+      else ptx::mbar_arrive(bar_wr);
+      if (rank == 0) {
+        ptx::mbar_wait(bar_wr, 0);
+        constexpr uint32_t IDESC = CG == 2 ? ptx::idesc_bf16(256, 256) : ptx::idesc_bf16(128, 128);
+        for (int t = 0; t < ntiles; ++t) {
+          const int as = t & 1;
+          ptx::mbar_wait(bar_acce(as), ((t >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          for (int c = 0; c < NCH; ++c) {
+            const int gc = t * NCH + c, s = gc % NSTAGE;
+            ptx::mbar_wait(bar_full(s), (gc / NSTAGE) & 1);
+            ptx::tc_fence_after();
+            const uint32_t a_hi = sbase + S::OFF_A + s * S::STAGE;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t acc_on = (c | ks) ? 1u : 0u;
+              const uint32_t kgw = (c * 4 + ks * 2) * W_KG;
+              const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 2 * A_KG, A_KG, 128);
+              const uint64_t da_lo = ptx::smem_desc(a_hi + A_HALF + ks * 2 * A_KG, A_KG, 128);
+              if constexpr (CG == 2) {
+                const uint32_t d = tmem + 256u * as;
+                const uint64_t db_hi = ptx::smem_desc(sbase + S::OFF_W + kgw, W_KG, 128);
+                ptx::mma_bf16<2>(d, da_hi, db_hi, IDESC, acc_on);
+                if constexpr (STRICT) {
+                  const uint64_t db_lo = ptx::smem_desc(sbase + S::OFF_W + W_HALF + kgw, W_KG, 128);
+                  ptx::mma_bf16<2>(d, da_hi, db_lo, IDESC, 1u);
+                  ptx::mma_bf16<2>(d, da_lo, db_hi, IDESC, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const uint32_t d = tmem + 256u * as + 128u * hf;
+                  const uint32_t wb = sbase + S::OFF_W + hf * (STRICT ? 2 : 1) * W_HALF;
+                  const uint64_t db_hi = ptx::smem_desc(wb + kgw, W_KG, 128);
+                  ptx::mma_bf16<1>(d, da_hi, db_hi, IDESC, acc_on);
+                  if constexpr (STRICT) {
+                    const uint64_t db_lo = ptx::smem_desc(wb + W_HALF + kgw, W_KG, 128);
+                    ptx::mma_bf16<1>(d, da_hi, db_lo, IDESC, 1u);
+                    ptx::mma_bf16<1>(d, da_lo, db_hi, IDESC, 1u);
+                  }
+                }
+              }
+            }
+            ptx::mma_commit<CG>(bar_empty(s));     // operand stage consumed (both CTAs)
+          }
+          ptx::mma_commit<CG>(bar_accf(as));       // accumulator complete (both CTAs)
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<CG>(tmem, 512);
+}
+
+__global__ void plan_k(const int32_t* __restrict__ sizes, int B, int32_t* __restrict__ row_off) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int acc = 0;
+  row_off[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = sizes[b];
+    acc += n * ((n + 7) & ~7);
+    row_off[b + 1] = acc;
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool GCL, bool STRICT, int CG>
+static int launch_edge(const Params& p, cudaStream_t st) {
+  using S = Smem<STRICT, CG>;
+  static bool configured = false;
+  auto kern = edge_tc_k<GCL, STRICT, CG>;
+  if (!configured) {
+    HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  int grid = sm_count();
+  if (CG == 2) grid &= ~1;
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+  return HD_OK;
+}
+
+}  // namespace tc
+
+bool tc_available() { return true; }
+
+int linear_fp32(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const float* WT,
+                int n_out, const float* bias, float* Y, int ldy, int mode, const float* resid);
+
+static int ensure_plan(const FwdCtx& c) {
+  if (c.B > tc::MAX_B) {
+    set_error("tensor-core engine supports at most %d molecules per call (got %d)", tc::MAX_B, c.B);
+    return HD_E_INVALID;
+  }
+  if (!c.planned) {
+    tc::plan_k<<<1, 32, 0, c.stream>>>(c.sizes, c.B, reinterpret_cast<int32_t*>(c.ws + c.W.row_off));
+    HD_CHECK_LAUNCH();
+    c.planned = true;
+  }
+  return HD_OK;
+}
+
+static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0, float* out, int engine) {
+  const SubLayer& S = c.L->subs[si];
+  auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  int rc = ensure_plan(c);
+  if (rc) return rc;
+  tc::Params p{};
+  p.ab = reinterpret_cast<const float*>(c.ws + c.W.ab);
+  p.x = x;
+  p.x0 = x0;
+  p.sizes = c.sizes;
+  p.row_off = reinterpret_cast<const int32_t*>(c.ws + c.W.row_off);
+  p.w_hi = c.packed + S.w2_hi;
+  p.w_lo = c.packed + S.w2_lo;
+  p.b2 = F(S.b2);
+  p.wa = F(S.wa);
+  p.ba = F(S.ba);
+  p.wr = F(S.wr);
+  p.wd = F(S.wd);
+  p.out = out;
+  p.B = c.B;
+  p.N = c.N;
+  p.attention = c.cfg->attention;
+  p.use_tanh = c.cfg->tanh;
+  p.range = c.cfg->coords_range / (float)c.cfg->n_layers;
+  p.norm_constant = c.cfg->norm_constant;
+  p.norm_div = c.cfg->aggregation_mean ? (float)c.N : c.cfg->normalization_factor;
+  const bool strict = engine == HD_ENGINE_TC_STRICT;
+  if (S.is_gcl) {
+    return strict ? tc::launch_edge<true, true, 2>(p, c.stream) : tc::launch_edge<true, false, 2>(p, c.stream);
+  }
+  HD_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 3 * c.B * c.N, c.stream));  // padded rows: x*mask = 0
+  return strict ? tc::launch_edge<false, true, 2>(p, c.stream) : tc::launch_edge<false, false, 2>(p, c.stream);
+}
+
+int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine) {
+  const SubLayer& S = c.L->subs[si];
+  auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
+  float* agg = reinterpret_cast<float*>(c.ws + c.W.agg);
+  float* hid = reinterpret_cast<float*>(c.ws + c.W.hid);
+  int rc;
+  if ((rc = linear_fp32(c, h, H, H, nullptr, 0, 0, F(S.w1abT), 2 * H, F(S.b1), ab, 2 * H, 0, nullptr))) return rc;
+  if ((rc = edge_launch(c, si, x, x0, agg, engine))) return rc;
+  if ((rc = linear_fp32(c, h, H, H, agg, H, H, F(S.v1T), H, F(S.c1), hid, H, 1, nullptr))) return rc;
+  return linear_fp32(c, hid, H, H, nullptr, 0, 0, F(S.v2T), H, F(S.c2), h, H, 2, h);
+}
+
+int tc_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out, int engine) {
+  const SubLayer& S = c.L->subs[si];
+  auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
+  int rc;
+  if ((rc = linear_fp32(c, h, H, H, nullptr, 0, 0, F(S.w1abT), 2 * H, F(S.b1), ab, 2 * H, 0, nullptr))) return rc;
+  return edge_launch(c, si, x, x0, x_out, engine);
+}
+
+int tc_edge_only(const FwdCtx& c, int si, const float* x, const float* x0, int engine) {
+  const SubLayer& S = c.L->subs[si];
+  float* out = reinterpret_cast<float*>(c.ws + (S.is_gcl ? c.W.agg : c.W.x2));
+  return edge_launch(c, si, x, x0, out, engine);
+}
+
 }  // namespace hd

@@ -130,9 +130,11 @@ def reverse_step_native(model, z_in, eps, rx, rh, sizes, gs, gt):
     flags = torch.zeros(1, dtype=torch.int32, device=dev())
     zs = torch.empty(B, N, D, device=dev())
     st = native.stream_ptr()
-    native.check(L.hd_step_scalars(native.ptr(cuda(gs)), native.ptr(cuda(gt)), B, native.ptr(sched), st), "scalars")
-    native.check(L.hd_reverse_step(native.ptr(cuda(z_in)), native.ptr(eps), native.ptr(cuda(rx)), native.ptr(cuda(rh)),
-                                   native.ptr(cuda(sizes, torch.int32)), B, N, D - 3, native.ptr(sched), 1,
+    # keep every temporary alive until the kernels ran: ptr() of a dead tensor would be recycled by the allocator
+    d_gs, d_gt, d_z, d_rx, d_rh, d_sz = cuda(gs), cuda(gt), cuda(z_in), cuda(rx), cuda(rh), cuda(sizes, torch.int32)
+    native.check(L.hd_step_scalars(native.ptr(d_gs), native.ptr(d_gt), B, native.ptr(sched), st), "scalars")
+    native.check(L.hd_reverse_step(native.ptr(d_z), native.ptr(eps), native.ptr(d_rx), native.ptr(d_rh),
+                                   native.ptr(d_sz), B, N, D - 3, native.ptr(sched), 1,
                                    native.ptr(zs), native.ptr(flags), st), "reverse_step")
     torch.cuda.synchronize()
     assert int(flags.item()) == 0
@@ -175,11 +177,12 @@ def test_final_decode_matches_reference_fixture(models, name):
     x = torch.empty(B, N, 3, device=dev())
     h = torch.empty(B, N, D - 3, device=dev())
     st = native.stream_ptr()
-    native.check(L.hd_final_scalars(native.ptr(cuda(g["gamma_out"][2 * T])), B, native.ptr(sched), st), "scalars")
-    native.check(L.hd_final_decode(native.ptr(cuda(z0)), native.ptr(eps), native.ptr(cuda(g["randn_x"][T + 1])),
-                                   native.ptr(cuda(g["randn_h"][T + 1])), native.ptr(cuda(sizes, torch.int32)), B, N,
-                                   D - 3, native.ptr(sched), 1, 1.0, 1.0, 0.0, native.ptr(x), native.ptr(h), st),
-                 "final_decode")
+    d_g0, d_z0, d_sz = cuda(g["gamma_out"][2 * T]), cuda(z0), cuda(sizes, torch.int32)
+    d_rx, d_rh = cuda(g["randn_x"][T + 1]), cuda(g["randn_h"][T + 1])
+    native.check(L.hd_final_scalars(native.ptr(d_g0), B, native.ptr(sched), st), "scalars")
+    native.check(L.hd_final_decode(native.ptr(d_z0), native.ptr(eps), native.ptr(d_rx), native.ptr(d_rh),
+                                   native.ptr(d_sz), B, N, D - 3, native.ptr(sched), 1, 1.0, 1.0, 0.0,
+                                   native.ptr(x), native.ptr(h), st), "final_decode")
     assert rel(x.cpu().numpy(), g["x"]) < 2e-5
     assert np.array_equal(h.cpu().numpy(), g["h"])
 
@@ -190,9 +193,9 @@ def test_combine_noise_matches_reference_fixture():
     sizes = g["sizes"]
     B, N = len(sizes), int(sizes.max())
     z = torch.empty(B, N, 11, device=dev())
-    native.check(native.lib().hd_combine_noise(native.ptr(cuda(g["randn_x"][0])), native.ptr(cuda(g["randn_h"][0])),
-                                               native.ptr(cuda(sizes, torch.int32)), B, N, 8, native.ptr(z),
-                                               native.stream_ptr()), "combine")
+    d_rx, d_rh, d_sz = cuda(g["randn_x"][0]), cuda(g["randn_h"][0]), cuda(sizes, torch.int32)
+    native.check(native.lib().hd_combine_noise(native.ptr(d_rx), native.ptr(d_rh), native.ptr(d_sz), B, N, 8,
+                                               native.ptr(z), native.stream_ptr()), "combine")
     want = masked_cog_noise(g["randn_x"][0], g["randn_h"][0], sizes)
     assert np.abs(z.cpu().numpy() - want).max() < 1e-6
 
