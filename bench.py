@@ -162,6 +162,7 @@ def run_ours(args):
         raise SystemExit(f"engine {engine} is not available in the native library")
     model.engine = engine
     model.steps_per_graph = args.steps_per_graph
+    model.use_cuda_graph = not args.no_graph
     torch.manual_seed(ctx.rank)                  # rank r samples with seed r
 
     B, N = B_PER_GPU, N_NODES
@@ -304,6 +305,7 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("HD_BENCH_ENGINE", "strict"), choices=["strict", "fast", "fp32"])
     ap.add_argument("--steps-per-graph", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the loop eagerly (profiling under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -170,7 +170,8 @@ class EGNN(nn.Module):
         k = (B, N, str(device))
         if k not in self._ws:
             nbytes = native.lib().hd_workspace_bytes(self.hd_config(), B, N)
-            self._ws = {k: torch.empty(nbytes, dtype=torch.uint8, device=device)}
+            # keep every shape's buffer: captured CUDA graphs hold raw pointers into them
+            self._ws[k] = torch.empty(nbytes, dtype=torch.uint8, device=device)
         return self._ws[k]
 
     def engine_id(self, engine=None):
