@@ -206,24 +206,24 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
       image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_w2, H, half * (H / 2), 0, H / 2, H, BF(S.w2_hi) + o,
                                              BF(S.w2_lo) + o);
     }
-    // W1ab as four 128-row quarters: rows 0..255 = h_i part (cols 0..H), rows 256..511 = h_j part
-    for (int q = 0; q < 4; ++q) {
-      const int64_t o = (int64_t)q * (H / 2) * H;
-      const int part = q / 2, row0 = (q % 2) * (H / 2);
-      image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_w1, ld1, row0, part * H, H / 2, H, BF(S.w1ab_hi) + o,
-                                             BF(S.w1ab_lo) + o);
+    // node-GEMM operand images (hd_node.cu): 64-row output tiles, img[tile][kg][64][8].
+    // W1ab: outputs 0..255 = h_i part (W1 cols 0..H), outputs 256..511 = h_j part (W1 cols H..2H)
+    for (int t = 0; t < 2 * H / 64; ++t) {
+      const int64_t o = (int64_t)t * 64 * H;
+      const int part = t / (H / 64), row0 = (t % (H / 64)) * 64;
+      image_k<<<grid(64 * H), T, 0, st>>>(w + S.s_w1, ld1, row0, part * H, 64, H, BF(S.w1ab_hi) + o,
+                                          BF(S.w1ab_lo) + o);
     }
     if (S.is_gcl) {
       transpose_k<<<grid(2 * H * H), T, 0, st>>>(w + S.s_v1, 2 * H, 0, H, 2 * H, F(S.v1T), H, 0);
       copy_k<<<grid(H), T, 0, st>>>(w + S.s_c1, H, F(S.c1));
       transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_v2, H, 0, H, H, F(S.v2T), H, 0);
       copy_k<<<grid(H), T, 0, st>>>(w + S.s_c2, H, F(S.c2));
-      for (int half = 0; half < 2; ++half) {
-        const int64_t o1 = (int64_t)half * (H / 2) * 2 * H, o2 = (int64_t)half * (H / 2) * H;
-        image_k<<<grid(H / 2 * 2 * H), T, 0, st>>>(w + S.s_v1, 2 * H, half * (H / 2), 0, H / 2, 2 * H,
-                                                   BF(S.v1_hi) + o1, BF(S.v1_lo) + o1);
-        image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_v2, H, half * (H / 2), 0, H / 2, H, BF(S.v2_hi) + o2,
-                                               BF(S.v2_lo) + o2);
+      for (int t = 0; t < H / 64; ++t) {
+        const int64_t o1 = (int64_t)t * 64 * 2 * H, o2 = (int64_t)t * 64 * H;
+        image_k<<<grid(64 * 2 * H), T, 0, st>>>(w + S.s_v1, 2 * H, t * 64, 0, 64, 2 * H, BF(S.v1_hi) + o1,
+                                                BF(S.v1_lo) + o1);
+        image_k<<<grid(64 * H), T, 0, st>>>(w + S.s_v2, H, t * 64, 0, 64, H, BF(S.v2_hi) + o2, BF(S.v2_lo) + o2);
       }
     }
   }
