@@ -551,9 +551,6 @@ static int launch_edge(const Params& p, cudaStream_t st) {
 
 bool tc_available() { return true; }
 
-int linear_fp32(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const float* WT,
-                int n_out, const float* bias, float* Y, int ldy, int mode, const float* resid);
-
 static int ensure_plan(const FwdCtx& c) {
   if (c.B > tc::MAX_B) {
     set_error("tensor-core engine supports at most %d molecules per call (got %d)", tc::MAX_B, c.B);
@@ -601,25 +598,38 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   return strict ? tc::launch_edge<false, true, 2>(p, c.stream) : tc::launch_edge<false, false, 2>(p, c.stream);
 }
 
+int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const void* w_hi,
+              const void* w_lo, int n_out, const float* bias, float* Y, int ldy, int mode, const float* resid,
+              bool strict);
+
+// A = h W1a^T + b1 ; B = h W1b^T  (packed b1 image is [b1 | 0], so the bias lands on the A half only)
+static int preproject(const FwdCtx& c, const SubLayer& S, const float* h, bool strict) {
+  float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
+  return linear_tc(c, h, H, H, nullptr, 0, 0, c.packed + S.w1ab_hi, c.packed + S.w1ab_lo, 2 * H,
+                   reinterpret_cast<const float*>(c.packed + S.b1), ab, 2 * H, 0, nullptr, strict);
+}
+
 int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine) {
   const SubLayer& S = c.L->subs[si];
   auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
-  float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
   float* agg = reinterpret_cast<float*>(c.ws + c.W.agg);
   float* hid = reinterpret_cast<float*>(c.ws + c.W.hid);
+  const bool strict = engine == HD_ENGINE_TC_STRICT;
   int rc;
-  if ((rc = linear_fp32(c, h, H, H, nullptr, 0, 0, F(S.w1abT), 2 * H, F(S.b1), ab, 2 * H, 0, nullptr))) return rc;
+  if ((rc = preproject(c, S, h, strict))) return rc;
   if ((rc = edge_launch(c, si, x, x0, agg, engine))) return rc;
-  if ((rc = linear_fp32(c, h, H, H, agg, H, H, F(S.v1T), H, F(S.c1), hid, H, 1, nullptr))) return rc;
-  return linear_fp32(c, hid, H, H, nullptr, 0, 0, F(S.v2T), H, F(S.c2), h, H, 2, h);
+  // node_model (egnn_new.py:52-62): h = (h + node_mlp([h, agg])) * node_mask
+  if ((rc = linear_tc(c, h, H, H, agg, H, H, c.packed + S.v1_hi, c.packed + S.v1_lo, H, F(S.c1), hid, H, 1, nullptr,
+                      strict)))
+    return rc;
+  return linear_tc(c, hid, H, H, nullptr, 0, 0, c.packed + S.v2_hi, c.packed + S.v2_lo, H, F(S.c2), h, H, 2, h,
+                   strict);
 }
 
 int tc_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out, int engine) {
   const SubLayer& S = c.L->subs[si];
-  auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
-  float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
   int rc;
-  if ((rc = linear_fp32(c, h, H, H, nullptr, 0, 0, F(S.w1abT), 2 * H, F(S.b1), ab, 2 * H, 0, nullptr))) return rc;
+  if ((rc = preproject(c, S, h, engine == HD_ENGINE_TC_STRICT))) return rc;
   return edge_launch(c, si, x, x0, x_out, engine);
 }
 
