@@ -297,6 +297,7 @@ def edge_kernel_roofline(model, loop, engine, B, N, iters=20):
 
 
 def main():
+    global T_STEPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -306,7 +307,10 @@ def main():
     ap.add_argument("--steps-per-graph", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the loop eagerly (profiling under ncu)")
+    ap.add_argument("--timesteps", type=int, default=T_STEPS,
+                    help="profiling only: a shorter chain (the JSON line then names the shortened workload)")
     args = ap.parse_args()
+    T_STEPS = args.timesteps
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -59,8 +59,8 @@ struct SubLayer {
   // tcgen05 operand images (bf16, canonical K-major no-swizzle core-matrix order):
   //   img[half][kg][n_local][8] with half<2, kg<H/8, n_local<H/2: element = W[half*H/2+n_local][kg*8+e]
   int64_t w2_hi, w2_lo;        // edge_mlp.2 / coord_mlp.2
-  // node-GEMM images (hd_node.cu): 64-row output tiles, img[tile][kg < K/8][64][8]
-  int64_t w1ab_hi, w1ab_lo;    // [2H out][H k] node pre-projection (8 tiles)
+  // node-GEMM images (hd_node.cu): img[tile][kg < K/8][tile rows][8], 128-row tiles for w1ab, 64-row for v1/v2
+  int64_t w1ab_hi, w1ab_lo;    // [2H out][H k] node pre-projection (4 tiles)
   int64_t v1_hi, v1_lo;        // [H out][2H k]  (GCL) node_mlp.0 (4 tiles, K = 2H)
   int64_t v2_hi, v2_lo;        // [H out][H k]   (GCL) node_mlp.2 (4 tiles)
 };

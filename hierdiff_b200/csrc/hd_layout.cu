@@ -206,13 +206,13 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
       image_k<<<grid(H / 2 * H), T, 0, st>>>(w + S.s_w2, H, half * (H / 2), 0, H / 2, H, BF(S.w2_hi) + o,
                                              BF(S.w2_lo) + o);
     }
-    // node-GEMM operand images (hd_node.cu): 64-row output tiles, img[tile][kg][64][8].
-    // W1ab: outputs 0..255 = h_i part (W1 cols 0..H), outputs 256..511 = h_j part (W1 cols H..2H)
-    for (int t = 0; t < 2 * H / 64; ++t) {
-      const int64_t o = (int64_t)t * 64 * H;
-      const int part = t / (H / 64), row0 = (t % (H / 64)) * 64;
-      image_k<<<grid(64 * H), T, 0, st>>>(w + S.s_w1, ld1, row0, part * H, 64, H, BF(S.w1ab_hi) + o,
-                                          BF(S.w1ab_lo) + o);
+    // node-GEMM operand images (hd_node.cu), img[tile][kg][tile rows][8].  W1ab in 128-row output tiles:
+    // outputs 0..255 = h_i part (W1 cols 0..H), outputs 256..511 = h_j part (W1 cols H..2H)
+    for (int t = 0; t < 2 * H / 128; ++t) {
+      const int64_t o = (int64_t)t * 128 * H;
+      const int part = t / (H / 128), row0 = (t % (H / 128)) * 128;
+      image_k<<<grid(128 * H), T, 0, st>>>(w + S.s_w1, ld1, row0, part * H, 128, H, BF(S.w1ab_hi) + o,
+                                           BF(S.w1ab_lo) + o);
     }
     if (S.is_gcl) {
       transpose_k<<<grid(2 * H * H), T, 0, st>>>(w + S.s_v1, 2 * H, 0, H, 2 * H, F(S.v1T), H, 0);

@@ -2,14 +2,15 @@
 // (the A|B pre-projection of edge_mlp.0 / coord_mlp.0, node_mlp.0, node_mlp.2; egnn_new.py:52-62 and SURVEY.md 7
 // "layer-1 split") as   Y[r, o] = epilogue(bias[o] + sum_k [X1 | X2][r, k] * W[o, k]).
 //
-//   tile     : 128 node rows x 64 output columns per CTA, K streamed in chunks of 64 through a 4-stage ring
-//   producer : 4 warps read the fp32 activations (L2-resident, written by the previous kernel), split them into
+//   tile     : 128 node rows x 64 or 128 output columns per CTA, K streamed in chunks of 64 through a 4-stage ring
+//   producer : 8 warps read the fp32 activations (L2-resident, written by the previous kernel), split them into
 //              bf16 hi (+ lo in strict mode) and store them as canonical K-major core matrices (the MMA A operand)
 //   weights  : 1 thread bulk-copies (TMA 1-D) the pre-built bf16 hi/lo image chunk of W for this column tile
 //   MMA      : 1 thread issues tcgen05.mma kind::f16 M=128 N=64 K=16; strict = hi*hi + hi*lo + lo*hi into one fp32
 //              TMEM accumulator (64 columns)
-//   epilogue : the 4 producer warps read the accumulator (thread = row): + bias, then store / SiLU /
-//              (resid + v) * node_mask
+//   epilogue : the 8 producer warps read the accumulator (thread = row, half of the columns): + bias, SiLU;
+//              the tile is staged in shared memory and written out coalesced, (resid + v) * node_mask applied
+//              on the way out with the residual rows prefetched before the accumulator wait
 //
 // Algorithmic HBM bytes: rows*(K + n_out)*4 activations + n_out*K*2(*2) weights; everything is L2-resident at the
 // sizes of the sampling path (h is 2.6 MB at B=64, N=40), so the kernel is bound by L2->SM latency/bandwidth.
@@ -21,24 +22,43 @@
 namespace hd {
 namespace lin {
 
-constexpr int TM = 128;                  // rows per CTA
-constexpr int NT = 64;                   // output columns per CTA
-constexpr int KC = 64;                   // K per stage
-constexpr int NSTG = 4;
-constexpr int A_KG = TM * 16;            // bytes between K-adjacent core matrices of the A stage image
-constexpr int A_PART = (KC / 8) * A_KG;  // 16 KB: hi (or lo) of one stage
-constexpr int W_KG = NT * 16;            // same for the weight image
-constexpr int W_PART = (KC / 8) * W_KG;  // 8 KB
-constexpr int NTHREADS = 192;            // 4 producer/epilogue warps + MMA warp + weight-copy warp
+// phase stamps for scripts/node_timing.cu (compiled out of the library)
+#ifdef HD_PHASE_TIMING
+__device__ unsigned long long g_phase[64];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define HD_STAMP(slot, cond) do { if ((cond) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) g_phase[slot] = gtimer(); } while (0)
+#else
+#define HD_STAMP(slot, cond) do { } while (0)
+#endif
 
-template <bool STRICT>
+constexpr int TM = 128;                  // rows per CTA
+constexpr int KC = 64;                   // K per stage
+constexpr int A_KG = TM * 16 + 16;       // bytes between K-adjacent core matrices of the A stage image (+16: the
+                                         // 8-byte producer stores of one row then spread over all banks)
+constexpr int A_PART = (KC / 8) * A_KG;  // ~16 KB: hi (or lo) of one stage
+constexpr int NPROD = 8;                 // producer / epilogue warps
+constexpr int NTHREADS = 32 * (NPROD + 2);   // + MMA warp + weight-copy warp
+
+// NT = output columns per CTA (64 or 128)
+template <bool STRICT, int NT>
 struct Smem {
   static constexpr int NP = STRICT ? 2 : 1;
-  static constexpr int STAGE = (A_PART + W_PART) * NP;   // [A_hi][A_lo][W_hi][W_lo]
-  static constexpr int OFF_BAR = NSTG * STAGE;           // full[NSTG], empty[NSTG], acc_full
+  static constexpr int NSTG = (STRICT && NT > 64) ? 3 : 4;   // ring depth (227 KB shared memory per CTA)
+  static constexpr int W_KG = NT * 16;            // bytes between K-adjacent core matrices of the weight image
+  static constexpr int W_PART = (KC / 8) * W_KG;  // hi (or lo) weight chunk of one stage
+  static constexpr int OT_LD = NT + 4;            // padded pitch (floats) of the output staging tile
+  static constexpr int STAGE = (A_PART + W_PART) * NP;   // [A_hi][A_lo][W_hi][W_lo]; the ring is reused as the
+                                                         // [TM][OT_LD] fp32 output staging tile after the last MMA
+  static constexpr int OFF_BIAS = NSTG * STAGE;          // [NT] fp32
+  static constexpr int OFF_BAR = OFF_BIAS + NT * 4;      // full[NSTG], empty[NSTG], acc_full
   static constexpr int NBAR = 2 * NSTG + 1;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
+  static_assert(TM * OT_LD * 4 <= NSTG * STAGE, "output staging tile must fit in the operand ring");
 };
 
 struct Params {
@@ -61,8 +81,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 template <bool STRICT>
+__device__ __forceinline__ float silu_node(float v) {
+  if constexpr (STRICT) {   // ex2.approx / rcp.approx, ~2 ulp each (same evaluation as the edge kernel)
+    return v * ptx::rcp_approx(1.0f + ptx::ex2_approx(-1.4426950408889634f * v));
+  } else {
+    const float hv = 0.5f * v;
+    return fmaf(hv, ptx::tanh_approx(hv), hv);
+  }
+}
+
+template <bool STRICT, int NT>
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
-  using S = Smem<STRICT>;
+  using S = Smem<STRICT, NT>;
+  constexpr int W_KG = S::W_KG, W_PART = S::W_PART, OT_LD = S::OT_LD, NSTG = S::NSTG;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -71,69 +102,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
   auto bar_empty = [&](int s) { return bar0 + 8u * (NSTG + s); };
   const uint32_t bar_acc = bar0 + 8u * (2 * NSTG);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
+  float* s_bias = reinterpret_cast<float*>(smem + S::OFF_BIAS);
 
   const int K = p.K1 + p.K2, nch = K / KC, nch1 = p.K1 / KC;
   const int row0 = blockIdx.x * TM, ct = blockIdx.y;
+  HD_STAMP(0, tid == 0);
 
   if (tid == 0) {
     for (int s = 0; s < NSTG; ++s) {
-      ptx::mbar_init(bar_full(s), 4 + 1);   // 4 producer warps + the weight copy's expect_tx arrive
-      ptx::mbar_init(bar_empty(s), 1);      // tcgen05.commit
+      ptx::mbar_init(bar_full(s), NPROD + 1);   // producer warps + the weight copy's expect_tx arrive
+      ptx::mbar_init(bar_empty(s), 1);          // tcgen05.commit
     }
     ptx::mbar_init(bar_acc, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 4) ptx::tmem_alloc<1>(sbase + S::OFF_TMEM, NT);
+  if (tid < NT) s_bias[tid] = p.bias ? p.bias[ct * NT + tid] : 0.f;
+  if (warp == NPROD) ptx::tmem_alloc<1>(sbase + S::OFF_TMEM, NT);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  HD_STAMP(1, tid == 0);
 
-  if (warp < 4) {
+  if (warp < NPROD) {
     // =========================== producers ===========================
-    const int rs = lane & 7, kq = lane >> 3;
-    auto load = [&](float4 (&v)[16], int c) {
+    // warp w converts rows [16w, 16w+16) of every K chunk; a warp-wide 16-byte load covers two full 256-byte row
+    // segments (fully coalesced), lane -> (row parity, 4 consecutive k)
+    const int l16 = lane & 15, rpar = lane >> 4;
+    auto load = [&](float4 (&v)[8], int c) {
       const bool first = c < nch1;
       const float* base = first ? p.X1 : p.X2;
       const int ld = first ? p.ld1 : p.ld2;
-      const int col = (first ? c : c - nch1) * KC;
+      const int col = (first ? c : c - nch1) * KC + 4 * l16;
 #pragma unroll
-      for (int rg = 0; rg < 4; ++rg) {
-        const int row = row0 + 32 * warp + 8 * rg + rs;
-        const float* q = base + (int64_t)row * ld + col + 8 * kq;
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {
-          if (row < p.rows) {
-            v[(rg * 2 + kh) * 2] = __ldg(reinterpret_cast<const float4*>(q + 32 * kh));
-            v[(rg * 2 + kh) * 2 + 1] = __ldg(reinterpret_cast<const float4*>(q + 32 * kh + 4));
-          } else {
-            v[(rg * 2 + kh) * 2] = v[(rg * 2 + kh) * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 16 * warp + 2 * i + rpar;
+        v[i] = row < p.rows ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)row * ld + col))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto convert_store = [&](const float4 (&v)[16], int s) {
-      uint8_t* stage = smem + s * S::STAGE;
+    auto convert_store = [&](const float4 (&v)[8], int s) {
+      uint8_t* dst0 = smem + s * S::STAGE + (l16 >> 1) * A_KG + (16 * warp + rpar) * 16 + (l16 & 1) * 8;
 #pragma unroll
-      for (int rg = 0; rg < 4; ++rg) {
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {
-          const float4 a = v[(rg * 2 + kh) * 2], b = v[(rg * 2 + kh) * 2 + 1];
-          uint4 hi;
-          hi.x = pack_bf16(a.x, a.y);
-          hi.y = pack_bf16(a.z, a.w);
-          hi.z = pack_bf16(b.x, b.y);
-          hi.w = pack_bf16(b.z, b.w);
-          uint8_t* dst = stage + (4 * kh + kq) * A_KG + (32 * warp + 8 * rg + rs) * 16;
-          *reinterpret_cast<uint4*>(dst) = hi;
-          if constexpr (STRICT) {
-            uint4 lo;
-            lo.x = pack_bf16(a.x - __uint_as_float(hi.x << 16), a.y - __uint_as_float(hi.x & 0xffff0000u));
-            lo.y = pack_bf16(a.z - __uint_as_float(hi.y << 16), a.w - __uint_as_float(hi.y & 0xffff0000u));
-            lo.z = pack_bf16(b.x - __uint_as_float(hi.z << 16), b.y - __uint_as_float(hi.z & 0xffff0000u));
-            lo.w = pack_bf16(b.z - __uint_as_float(hi.w << 16), b.w - __uint_as_float(hi.w & 0xffff0000u));
-            *reinterpret_cast<uint4*>(dst + A_PART) = lo;
-          }
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = v[i];
+        uint2 hi;
+        hi.x = pack_bf16(a.x, a.y);
+        hi.y = pack_bf16(a.z, a.w);
+        *reinterpret_cast<uint2*>(dst0 + 32 * i) = hi;
+        if constexpr (STRICT) {
+          uint2 lo;
+          lo.x = pack_bf16(a.x - __uint_as_float(hi.x << 16), a.y - __uint_as_float(hi.x & 0xffff0000u));
+          lo.y = pack_bf16(a.z - __uint_as_float(hi.y << 16), a.w - __uint_as_float(hi.y & 0xffff0000u));
+          *reinterpret_cast<uint2*>(dst0 + 32 * i + A_PART) = lo;
         }
       }
     };
@@ -142,63 +163,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_full(s));
     };
-    float4 va[16], vb[16];
-    load(va, 0);
-    if (nch > 1) load(vb, 1);
+    // four chunks of loads in flight per thread (the whole ring)
+    float4 v0[8], v1[8], v2[8], v3[8];
+    load(v0, 0);
+    if (nch > 1) load(v1, 1);
+    if (nch > 2) load(v2, 2);
+    if (nch > 3) load(v3, 3);
 #pragma unroll 1
-    for (int c = 0; c < nch; c += 2) {   // nch is even (K1, K2 multiples of 128) or 1.. handled by guards
-      {
-        const int s = c % NSTG;
-        ptx::mbar_wait(bar_empty(s), ((c / NSTG) & 1) ^ 1);
-        convert_store(va, s);
-        if (c + 2 < nch) load(va, c + 2);
+    for (int c = 0; c < nch; c += 4) {
+      auto step = [&](float4 (&v)[8], int cc) {
+        if (cc >= nch) return;
+        const int s = cc % NSTG;
+        ptx::mbar_wait(bar_empty(s), ((cc / NSTG) & 1) ^ 1);
+        convert_store(v, s);
+        if (cc + 4 < nch) load(v, cc + 4);
         publish(s);
-      }
-      if (c + 1 < nch) {
-        const int s = (c + 1) % NSTG;
-        ptx::mbar_wait(bar_empty(s), (((c + 1) / NSTG) & 1) ^ 1);
-        convert_store(vb, s);
-        if (c + 3 < nch) load(vb, c + 3);
-        publish(s);
+      };
+      step(v0, c);
+      step(v1, c + 1);
+      step(v2, c + 2);
+      step(v3, c + 3);
+    }
+    HD_STAMP(6, tid == 0);
+    // residual rows, fetched coalesced while the last MMAs run: pass q covers rows [RPP*q, RPP*q + RPP)
+    constexpr int TPR = NT / 4, RPP = 32 * NPROD / TPR, NPASS = TM / RPP;   // threads per row, rows per pass
+    const int orow = tid / TPR, oc4 = (tid % TPR) * 4;
+    float4 rr[NPASS];
+    if (p.mode == 2) {
+#pragma unroll
+      for (int q = 0; q < NPASS; ++q) {
+        const int row = row0 + RPP * q + orow;
+        rr[q] = row < p.rows ? *reinterpret_cast<const float4*>(p.resid + (int64_t)row * p.ldy + ct * NT + oc4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    // =========================== epilogue ===========================
     ptx::mbar_wait(bar_acc, 0);
     ptx::tc_fence_after();
-    const int row = row0 + 32 * warp + lane;
-    const bool in_rows = row < p.rows;
-    bool real = true;
-    if (p.mode == 2 && in_rows) real = (row % p.N) < p.sizes[row / p.N];
-    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    HD_STAMP(7, tid == 0);
+    {
+      // thread = accumulator row (TMEM lane), warp -> lane quarter (warp % 4) and column half (warp / 4)
+      const int lq = warp & 3, ch = warp >> 2;
+      float* trow = reinterpret_cast<float*>(smem) + (32 * lq + lane) * OT_LD + (NT / 2) * ch;
 #pragma unroll 1
-    for (int half = 0; half < NT / 32; ++half) {
-      float v[32];
-      ptx::tmem_ld32(taddr + 32 * half, v);
-      ptx::tmem_wait_ld();
-      const int col = ct * NT + 32 * half;
-      float* yrow = p.Y + (int64_t)row * p.ldy + col;
-      const float* rrow = p.resid + (int64_t)row * p.ldy + col;
+      for (int part = 0; part < NT / 64; ++part) {
+        float v[32];
+        ptx::tmem_ld32(tmem + ((uint32_t)(32 * lq) << 16) + (NT / 2) * ch + 32 * part, v);
+        ptx::tmem_wait_ld();
 #pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        float4 o = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-        if (p.bias) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * k4));
-          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-        }
-        if (p.mode == 1) {
-          o.x = silu_acc(o.x); o.y = silu_acc(o.y); o.z = silu_acc(o.z); o.w = silu_acc(o.w);
-        } else if (p.mode == 2) {
-          if (in_rows && real) {
-            const float4 rr = *reinterpret_cast<const float4*>(rrow + 4 * k4);
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          } else {
-            o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + (NT / 2) * ch + 32 * part + 4 * k4);
+          float4 o = make_float4(v[4 * k4] + bb.x, v[4 * k4 + 1] + bb.y, v[4 * k4 + 2] + bb.z, v[4 * k4 + 3] + bb.w);
+          if (p.mode == 1) {
+            o.x = silu_node<STRICT>(o.x); o.y = silu_node<STRICT>(o.y);
+            o.z = silu_node<STRICT>(o.z); o.w = silu_node<STRICT>(o.w);
           }
+          *reinterpret_cast<float4*>(trow + 32 * part + 4 * k4) = o;
         }
-        if (in_rows) *reinterpret_cast<float4*>(yrow + 4 * k4) = o;
       }
     }
-  } else if (warp == 4) {
+    ptx::named_bar_sync(1, 32 * NPROD);
+    HD_STAMP(8, tid == 0);
+#pragma unroll
+    for (int q = 0; q < NPASS; ++q) {
+      const int row = row0 + RPP * q + orow;
+      if (row >= p.rows) continue;
+      float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + (RPP * q + orow) * OT_LD + oc4);
+      if (p.mode == 2) {
+        if ((row % p.N) < p.sizes[row / p.N]) {
+          o.x += rr[q].x; o.y += rr[q].y; o.z += rr[q].z; o.w += rr[q].w;
+        } else {
+          o = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + ct * NT + oc4) = o;
+    }
+  } else if (warp == NPROD) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t IDESC = ptx::idesc_bf16(TM, NT);
@@ -206,6 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
         const int s = c % NSTG;
         ptx::mbar_wait(bar_full(s), (c / NSTG) & 1);
         ptx::tc_fence_after();
+        HD_STAMP(16 + c, true);
         const uint32_t a_hi = sbase + s * S::STAGE, a_lo = a_hi + A_PART;
         const uint32_t w_hi = a_hi + S::NP * A_PART, w_lo = w_hi + W_PART;
 #pragma unroll
@@ -243,16 +283,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
     __syncwarp();
   }
 
+  HD_STAMP(9, tid == 0);
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc<1>(tmem, NT);
+  if (warp == NPROD) ptx::tmem_dealloc<1>(tmem, NT);
+  HD_STAMP(10, tid == 32 * NPROD);
 }
 
-template <bool STRICT>
+template <bool STRICT, int NT>
 static int launch(const Params& p, int n_out, cudaStream_t st) {
-  using S = Smem<STRICT>;
+  using S = Smem<STRICT, NT>;
   static bool configured = false;
-  auto kern = linear_tc_k<STRICT>;
+  auto kern = linear_tc_k<STRICT, NT>;
   if (!configured) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
@@ -265,12 +307,15 @@ static int launch(const Params& p, int n_out, cudaStream_t st) {
 
 }  // namespace lin
 
-// Y = epilogue([X1 | X2] W^T + bias) on the tensor cores; W given as its bf16 hi/lo tile images (hd_layout.cu)
+// Y = epilogue([X1 | X2] W^T + bias) on the tensor cores; W given as its bf16 hi/lo images in `tile_n`-row output
+// tiles (hd_layout.cu): tile_n = 128 for the 512-wide pre-projection, 64 for the 256-wide node_mlp layers, so that
+// every launch is a single wave of CTAs at the sampling path's batch sizes
 int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const void* w_hi,
-              const void* w_lo, int n_out, const float* bias, float* Y, int ldy, int mode, const float* resid,
-              bool strict) {
-  if (K1 % lin::KC || K2 % lin::KC || n_out % lin::NT || (ld1 & 3) || (ld2 & 3) || (ldy & 3)) {
-    set_error("linear_tc: unsupported shape K1=%d K2=%d n_out=%d", K1, K2, n_out);
+              const void* w_lo, int n_out, int tile_n, const float* bias, float* Y, int ldy, int mode,
+              const float* resid, bool strict) {
+  if (K1 % lin::KC || K2 % lin::KC || (tile_n != 64 && tile_n != 128) || n_out % tile_n || (ld1 & 3) || (ld2 & 3) ||
+      (ldy & 3)) {
+    set_error("linear_tc: unsupported shape K1=%d K2=%d n_out=%d tile_n=%d", K1, K2, n_out, tile_n);
     return HD_E_INVALID;
   }
   lin::Params p{};
@@ -290,7 +335,8 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
   p.resid = resid ? resid : Y;
   p.sizes = c.sizes;
   p.N = c.N;
-  return strict ? lin::launch<true>(p, n_out, c.stream) : lin::launch<false>(p, n_out, c.stream);
+  if (tile_n == 128) return strict ? lin::launch<true, 128>(p, n_out, c.stream) : lin::launch<false, 128>(p, n_out, c.stream);
+  return strict ? lin::launch<true, 64>(p, n_out, c.stream) : lin::launch<false, 64>(p, n_out, c.stream);
 }
 
 }  // namespace hd

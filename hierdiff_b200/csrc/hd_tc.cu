@@ -599,13 +599,13 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
 }
 
 int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const void* w_hi,
-              const void* w_lo, int n_out, const float* bias, float* Y, int ldy, int mode, const float* resid,
-              bool strict);
+              const void* w_lo, int n_out, int tile_n, const float* bias, float* Y, int ldy, int mode,
+              const float* resid, bool strict);
 
 // A = h W1a^T + b1 ; B = h W1b^T  (packed b1 image is [b1 | 0], so the bias lands on the A half only)
 static int preproject(const FwdCtx& c, const SubLayer& S, const float* h, bool strict) {
   float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
-  return linear_tc(c, h, H, H, nullptr, 0, 0, c.packed + S.w1ab_hi, c.packed + S.w1ab_lo, 2 * H,
+  return linear_tc(c, h, H, H, nullptr, 0, 0, c.packed + S.w1ab_hi, c.packed + S.w1ab_lo, 2 * H, 128,
                    reinterpret_cast<const float*>(c.packed + S.b1), ab, 2 * H, 0, nullptr, strict);
 }
 
@@ -619,10 +619,10 @@ int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, i
   if ((rc = preproject(c, S, h, strict))) return rc;
   if ((rc = edge_launch(c, si, x, x0, agg, engine))) return rc;
   // node_model (egnn_new.py:52-62): h = (h + node_mlp([h, agg])) * node_mask
-  if ((rc = linear_tc(c, h, H, H, agg, H, H, c.packed + S.v1_hi, c.packed + S.v1_lo, H, F(S.c1), hid, H, 1, nullptr,
+  if ((rc = linear_tc(c, h, H, H, agg, H, H, c.packed + S.v1_hi, c.packed + S.v1_lo, H, 64, F(S.c1), hid, H, 1, nullptr,
                       strict)))
     return rc;
-  return linear_tc(c, hid, H, H, nullptr, 0, 0, c.packed + S.v2_hi, c.packed + S.v2_lo, H, F(S.c2), h, H, 2, h,
+  return linear_tc(c, hid, H, H, nullptr, 0, 0, c.packed + S.v2_hi, c.packed + S.v2_lo, H, 64, F(S.c2), h, H, 2, h,
                    strict);
 }
 
