@@ -69,7 +69,8 @@ struct Params {
   const void* w_lo;
   const float* bias;      // [n_out] or null
   float* Y;
-  int ldy, rows, mode;    // mode 0: store, 1: SiLU, 2: (resid + v) * node_mask
+  int ldy, rows, mode;    // mode 0: store, 1: SiLU, 2: (resid + v) * node_mask, 3: store K-chunk-major
+                          // Y[col/16][row][col%16] (the edge kernel's A|B operand layout)
   const float* resid;
   const int32_t* sizes;
   int N;
@@ -235,7 +236,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
           o = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + ct * NT + oc4) = o;
+      const int col = ct * NT + oc4;
+      if (p.mode == 3) *reinterpret_cast<float4*>(p.Y + ((int64_t)(col >> 4) * p.rows + row) * 16 + (col & 15)) = o;
+      else *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + col) = o;
     }
   } else if (warp == NPROD) {
     // =========================== MMA issuer ===========================

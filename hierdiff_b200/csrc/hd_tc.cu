@@ -33,20 +33,27 @@ constexpr int A_KG = 2048;            // bytes between K-adjacent core matrices 
 constexpr int A_HALF = 4 * A_KG;      // one stage of hi (or lo): 4 core-matrix columns = 8 KB
 constexpr int W_KG = 2048;            // bytes between K-adjacent core matrices of a 128-row W half image
 constexpr int W_HALF = (H / 8) * W_KG;  // 64 KB: one 128-row half image (hi or lo)
-constexpr int META_BUFS = 3;
-constexpr int GRP_BUFS = 4;           // per-tile group table ring (receiver of each 8-row group)
-constexpr int MAX_B = 511;            // molecules per launch (row_off table in shared memory)
-constexpr int NTHREADS = 288;         // 4 producer + 4 epilogue + 1 MMA/alloc warp
+constexpr int PMETA_BUFS = 2;         // producer-side row metadata: tiles t, t+1
+constexpr int EMETA_BUFS = 4;         // epilogue-side row metadata / group table: tiles t-2 .. t+1
+constexpr int MAX_B = 255;            // molecules per launch (row_off table in shared memory)
+constexpr int NPW = 8;                // producer warps
+constexpr int NEW = 8;                // epilogue warps
+constexpr int PROD_THREADS = 32 * NPW, EPI_THREADS = 32 * NEW;
+constexpr int NTHREADS = PROD_THREADS + EPI_THREADS + 32;   // + 1 MMA/alloc warp
 
-struct RowMeta {      // 32 bytes per edge row of a tile
+struct PMeta {        // what the operand producers need of an edge row
   float r, d0;        // |x_i-x_j|^2, |x0_i-x0_j|^2
   int recv, send;     // flat node rows b*N+i, b*N+j
+};
+struct EMeta {        // what the epilogue needs of an edge row
   float cd0, cd1, cd2;  // (x_i-x_j)/(sqrt(r+1e-8)+norm_constant)  (EquivariantUpdate only)
   int flags;          // bit0: row is a real edge slot (j<n, inside this CTA's range); bit1: j==i
 };
 
 struct Params {
-  const float* ab;     // [BN][2H]  A_i (+b1) | B_j
+  const float* a_img;  // [H/16][BN][16]  A_i (+b1), K-chunk-major so that 8 consecutive nodes x 16 columns are 512 B
+  const float* b_img;  // [H/16][BN][16]  B_j
+  int64_t kc_stride;   // BN*16 floats between 16-column chunks
   const float* x;      // [BN][3] block-entry coordinates
   const float* x0;     // [BN][3] EGNN-entry coordinates
   const int32_t* sizes;
@@ -69,13 +76,16 @@ struct Smem {
   static constexpr int OFF_SCR = OFF_A + NSTAGE * STAGE;           // [16][H] fp32
   static constexpr int OFF_VEC = OFF_SCR + 16 * H * 4;             // b2, wa, wr, wd
   static constexpr int OFF_ROW = OFF_VEC + 4 * H * 4;              // row_off [MAX_B+1]
-  static constexpr int OFF_META = OFF_ROW + (MAX_B + 1) * 4;
-  static constexpr int OFF_GRP = OFF_META + META_BUFS * TILE_M * (int)sizeof(RowMeta);   // int2 [GRP_BUFS][16]
-  static constexpr int OFF_BAR = OFF_GRP + GRP_BUFS * 16 * 8;
+  static constexpr int OFF_PMETA = OFF_ROW + (MAX_B + 1) * 4;
+  static constexpr int OFF_EMETA = OFF_PMETA + PMETA_BUFS * TILE_M * (int)sizeof(PMeta);
+  static constexpr int OFF_GRP = OFF_EMETA + EMETA_BUFS * TILE_M * (int)sizeof(EMeta);   // int2 [EMETA_BUFS][16]
+  static constexpr int OFF_DOT = OFF_GRP + EMETA_BUFS * 16 * 8;    // [2][TILE_M] partial attention dots
+  static constexpr int OFF_BAR = OFF_DOT + 2 * TILE_M * 4;
   // barriers: full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2], w_local, w_ready ; then tmem ptr
   static constexpr int NBAR = 2 * NSTAGE + 6;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
+  static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 // largest b with row_off[b] <= R  (row_off[0] = 0, row_off[B] = total > R)
@@ -123,8 +133,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   float* s_wr = s_wa + H;
   float* s_wd = s_wr + H;
   int* s_row = reinterpret_cast<int*>(smem + S::OFF_ROW);
-  RowMeta* s_meta = reinterpret_cast<RowMeta*>(smem + S::OFF_META);
+  PMeta* s_pmeta = reinterpret_cast<PMeta*>(smem + S::OFF_PMETA);
+  EMeta* s_emeta = reinterpret_cast<EMeta*>(smem + S::OFF_EMETA);
   int2* s_grp = reinterpret_cast<int2*>(smem + S::OFF_GRP);   // {receiver row, group is inside this CTA's range}
+  float* s_dot = reinterpret_cast<float*>(smem + S::OFF_DOT);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
   const uint32_t bar0 = sbase + S::OFF_BAR;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -132,6 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   auto bar_accf = [&](int a) { return bar0 + 8u * (2 * NSTAGE + a); };
   auto bar_acce = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
   const uint32_t bar_wl = bar0 + 8u * (2 * NSTAGE + 4), bar_wr = bar0 + 8u * (2 * NSTAGE + 5);
+  constexpr int MMA_WARP = NPW + NEW;
 
   // ---- one-time setup --------------------------------------------------------------------------
   for (int k = tid; k < H; k += NTHREADS) {
@@ -143,18 +156,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      ptx::mbar_init(bar_full(s), 4 * CG);   // one elected arrive per producer warp of each CTA
-      ptx::mbar_init(bar_empty(s), 1);       // tcgen05.commit
+      ptx::mbar_init(bar_full(s), NPW * CG);   // one elected arrive per producer warp of each CTA
+      ptx::mbar_init(bar_empty(s), 1);         // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(bar_accf(a), 1);        // tcgen05.commit
-      ptx::mbar_init(bar_acce(a), 4 * CG);   // one elected arrive per epilogue warp of each CTA
+      ptx::mbar_init(bar_accf(a), 1);          // tcgen05.commit
+      ptx::mbar_init(bar_acce(a), NEW * CG);   // one elected arrive per epilogue warp of each CTA
     }
     ptx::mbar_init(bar_wl, 1);
     ptx::mbar_init(bar_wr, CG);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
+  if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
@@ -177,99 +190,99 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     ntiles = max(ntiles, (pe - pa + TILE_M - 1) / TILE_M);
   }
 
-  if (warp < 4) {
+  if (warp < NPW) {
     // =========================== producers ===========================
-    const int rsub = (lane >> 1) & 7;                 // row within an 8-row group
-    const int qsub = 2 * (lane >> 4) + (lane & 1);    // 16-byte quad within a 16-column half stage
-    for (int t = 0; t < ntiles; ++t) {
-      RowMeta* meta = s_meta + (t % META_BUFS) * TILE_M;
-      {  // row metadata of tile row `tid`
-        const int R = row_begin + t * TILE_M + tid;
-        RowMeta m;
-        m.r = m.d0 = m.cd0 = m.cd1 = m.cd2 = 0.f;
-        m.recv = m.send = 0;
-        m.flags = 0;
-        if (R < row_end) {
-          const int b = find_mol(s_row, p.B, R);
-          const int n = p.sizes[b], npad = (n + 7) & ~7;
-          const int local = R - s_row[b];
-          const int i = local / npad, j = local - i * npad;
-          m.recv = b * p.N + i;
-          m.send = m.recv;
-          if (j < n) {
-            m.send = b * p.N + j;
-            m.flags = 1 | (j == i ? 2 : 0);
-            const float* xi = p.x + 3 * (int64_t)m.recv;
-            const float* xj = p.x + 3 * (int64_t)m.send;
-            const float* oi = p.x0 + 3 * (int64_t)m.recv;
-            const float* oj = p.x0 + 3 * (int64_t)m.send;
-            const float d0 = xi[0] - xj[0], d1 = xi[1] - xj[1], d2 = xi[2] - xj[2];
-            const float e0 = oi[0] - oj[0], e1 = oi[1] - oj[1], e2 = oi[2] - oj[2];
-            m.r = d0 * d0 + d1 * d1 + d2 * d2;
-            m.d0 = e0 * e0 + e1 * e1 + e2 * e2;
-            if (!GCL) {
-              const float nrm = sqrtf(m.r + 1e-8f) + p.norm_constant;
-              m.cd0 = d0 / nrm;
-              m.cd1 = d1 / nrm;
-              m.cd2 = d2 / nrm;
-            }
-          } else {
-            m.flags = 4;  // padding slot inside a real receiver's group
+    // warp w builds rows [16w, 16w+16) of every operand stage: lane -> (row in 8-group, 4 columns of a 16-column half)
+    const int rsub = (lane >> 1) & 7;
+    const int qsub = 2 * (lane >> 4) + (lane & 1);
+    // metadata of tile row `tid` of tile t (threads 0..127), one tile ahead of its use
+    auto make_meta = [&](int t) {
+      const int R = row_begin + t * TILE_M + tid;
+      PMeta m;
+      EMeta e;
+      m.r = m.d0 = e.cd0 = e.cd1 = e.cd2 = 0.f;
+      m.recv = m.send = 0;
+      e.flags = 0;
+      if (R < row_end) {
+        const int b = find_mol(s_row, p.B, R);
+        const int n = p.sizes[b], npad = (n + 7) & ~7;
+        const int local = R - s_row[b];
+        const int i = local / npad, j = local - i * npad;
+        m.recv = b * p.N + i;
+        m.send = m.recv;
+        if (j < n) {
+          m.send = b * p.N + j;
+          e.flags = 1 | (j == i ? 2 : 0);
+          const float* xi = p.x + 3 * (int64_t)m.recv;
+          const float* xj = p.x + 3 * (int64_t)m.send;
+          const float* oi = p.x0 + 3 * (int64_t)m.recv;
+          const float* oj = p.x0 + 3 * (int64_t)m.send;
+          const float d0 = xi[0] - xj[0], d1 = xi[1] - xj[1], d2 = xi[2] - xj[2];
+          const float e0 = oi[0] - oj[0], e1 = oi[1] - oj[1], e2 = oi[2] - oj[2];
+          m.r = d0 * d0 + d1 * d1 + d2 * d2;
+          m.d0 = e0 * e0 + e1 * e1 + e2 * e2;
+          if (!GCL) {
+            const float nrm = sqrtf(m.r + 1e-8f) + p.norm_constant;
+            e.cd0 = d0 / nrm;
+            e.cd1 = d1 / nrm;
+            e.cd2 = d2 / nrm;
           }
+        } else {
+          e.flags = 4;  // padding slot inside a real receiver's group (operand row = A_i + B_i: finite, masked later)
         }
-        meta[tid] = m;
-        if ((tid & 7) == 0) s_grp[(t % GRP_BUFS) * 16 + (tid >> 3)] = make_int2(m.recv, m.flags != 0);
       }
-      ptx::named_bar_sync(1, 128);
-      // the 4 rows this thread feeds: 32*warp + 8*rb + rsub
-      float rr[4], dd[4];
-      const float* pa[4];
-      const float* pb[4];
-      bool ok[4];
+      s_pmeta[(t % PMETA_BUFS) * TILE_M + tid] = m;
+      s_emeta[(t % EMETA_BUFS) * TILE_M + tid] = e;
+      if ((tid & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (tid >> 3)] = make_int2(m.recv, e.flags != 0);
+    };
+    if (tid < TILE_M && ntiles > 0) make_meta(0);
+    ptx::named_bar_sync(1, PROD_THREADS);
+    for (int t = 0; t < ntiles; ++t) {
+      const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
+      // the 2 rows this thread feeds: 16*warp + 8*rb + rsub
+      float rr[2], dd[2];
+      const float* pa[2];
+      const float* pb[2];
 #pragma unroll
-      for (int rb = 0; rb < 4; ++rb) {
-        const RowMeta& m = meta[32 * warp + 8 * rb + rsub];
+      for (int rb = 0; rb < 2; ++rb) {
+        const PMeta m = meta[16 * warp + 8 * rb + rsub];
         rr[rb] = m.r;
         dd[rb] = m.d0;
-        ok[rb] = (m.flags & 1) != 0;
-        pa[rb] = p.ab + (int64_t)m.recv * (2 * H) + 4 * qsub;
-        pb[rb] = p.ab + (int64_t)m.send * (2 * H) + H + 4 * qsub;
+        pa[rb] = p.a_img + (int64_t)m.recv * 16 + 4 * qsub;
+        pb[rb] = p.b_img + (int64_t)m.send * 16 + 4 * qsub;
       }
-      // software pipeline over half stages (16 K-columns): the loads of the next half stage are in flight
-      // while the current one is computed
-      float4 va0[4], vb0[4], va1[4], vb1[4];
-      auto load_half = [&](float4 (&va)[4], float4 (&vb)[4], int hs) {
+      // software pipeline over half stages (16 K-columns), loads issued 3 half stages ahead of their use
+      float4 v0[4], v1[4], v2[4], v3[4];   // {A row0, A row1, B row0, B row1}
+      auto load_half = [&](float4 (&v)[4], int hs) {
+        const int64_t o = hs * p.kc_stride;
 #pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-          va[rb] = __ldg(reinterpret_cast<const float4*>(pa[rb] + 16 * hs));
-          vb[rb] = __ldg(reinterpret_cast<const float4*>(pb[rb] + 16 * hs));
+        for (int rb = 0; rb < 2; ++rb) {
+          v[rb] = __ldg(reinterpret_cast<const float4*>(pa[rb] + o));
+          v[2 + rb] = __ldg(reinterpret_cast<const float4*>(pb[rb] + o));
         }
       };
-      auto half_step = [&](const float4 (&va)[4], const float4 (&vb)[4], int c, int ph, int s) {
-        const int k0 = 32 * c + 16 * ph + 4 * qsub;
+      auto half_step = [&](const float4 (&v)[4], int hs, int s) {
+        const int ph = hs & 1;
+        const int k0 = 16 * hs + 4 * qsub;
         const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
         const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
         uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8;
 #pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-          const float4 a = va[rb], b = vb[rb];
-          float v0 = fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x));
-          float v1 = fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y));
-          float v2 = fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z));
-          float v3 = fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w));
-          v0 = ok[rb] ? silu_edge<STRICT>(v0) : 0.f;
-          v1 = ok[rb] ? silu_edge<STRICT>(v1) : 0.f;
-          v2 = ok[rb] ? silu_edge<STRICT>(v2) : 0.f;
-          v3 = ok[rb] ? silu_edge<STRICT>(v3) : 0.f;
-          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+        for (int rb = 0; rb < 2; ++rb) {
+          const float4 a = v[rb], b = v[2 + rb];
+          const float m0 = silu_edge<STRICT>(fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x)));
+          const float m1 = silu_edge<STRICT>(fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y)));
+          const float m2 = silu_edge<STRICT>(fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z)));
+          const float m3 = silu_edge<STRICT>(fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w)));
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
           uint2 hi;
           hi.x = *reinterpret_cast<const uint32_t*>(&h01);
           hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-          uint8_t* dst = stage + (32 * warp + 8 * rb + rsub) * 16;
+          uint8_t* dst = stage + (16 * warp + 8 * rb + rsub) * 16;
           *reinterpret_cast<uint2*>(dst) = hi;
           if constexpr (STRICT) {
-            const float l0 = v0 - __uint_as_float(hi.x << 16), l1 = v1 - __uint_as_float(hi.x & 0xffff0000u);
-            const float l2 = v2 - __uint_as_float(hi.y << 16), l3 = v3 - __uint_as_float(hi.y & 0xffff0000u);
+            const float l0 = m0 - __uint_as_float(hi.x << 16), l1 = m1 - __uint_as_float(hi.x & 0xffff0000u);
+            const float l2 = m2 - __uint_as_float(hi.y << 16), l3 = m3 - __uint_as_float(hi.y & 0xffff0000u);
             const __nv_bfloat162 g01 = __floats2bfloat162_rn(l0, l1), g23 = __floats2bfloat162_rn(l2, l3);
             uint2 lo;
             lo.x = *reinterpret_cast<const uint32_t*>(&g01);
@@ -278,59 +291,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           }
         }
       };
-      load_half(va0, vb0, 0);
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const int gc = t * NCH + c, s = gc % NSTAGE;
-        load_half(va1, vb1, 2 * c + 1);
-        ptx::mbar_wait(bar_empty(s), ((gc / NSTAGE) & 1) ^ 1);
-        half_step(va0, vb0, c, 0, s);
-        if (c + 1 < NCH) load_half(va0, vb0, 2 * c + 2);
-        half_step(va1, vb1, c, 1, s);
+      auto publish = [&](int s) {
         ptx::fence_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_full(s), 0);
           else ptx::mbar_arrive(bar_full(s));
         }
+      };
+      load_half(v0, 0);
+      load_half(v1, 1);
+      load_half(v2, 2);
+      // next tile's row metadata while the first loads are in flight
+      if (tid < TILE_M && t + 1 < ntiles) make_meta(t + 1);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        const int gc = t * NCH + c, sa = gc % NSTAGE, sb = (gc + 1) % NSTAGE;
+        load_half(v3, 2 * c + 3);
+        ptx::mbar_wait(bar_empty(sa), ((gc / NSTAGE) & 1) ^ 1);
+        half_step(v0, 2 * c, sa);
+        if (c + 2 < NCH) load_half(v0, 2 * c + 4);
+        half_step(v1, 2 * c + 1, sa);
+        publish(sa);
+        if (c + 2 < NCH) load_half(v1, 2 * c + 5);
+        ptx::mbar_wait(bar_empty(sb), (((gc + 1) / NSTAGE) & 1) ^ 1);
+        half_step(v2, 2 * c + 2, sb);
+        if (c + 2 < NCH) load_half(v2, 2 * c + 6);
+        half_step(v3, 2 * c + 3, sb);
+        publish(sb);
       }
+      ptx::named_bar_sync(1, PROD_THREADS);   // metadata of tile t+1 complete (and tile t's no longer read)
     }
-  } else if (warp < 8) {
+  } else if (warp < MMA_WARP) {
     // =========================== epilogue ===========================
-    const int q = warp - 4, etid = tid - 128;
-    const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
-    float carry0 = 0.f, carry1 = 0.f;
+    // warp -> TMEM lane quarter q (= warp % 4) and column half; thread = edge row, 128 of the 256 columns
+    const int ew = warp - NPW, q = ew & 3, half = ew >> 2, etid = tid - PROD_THREADS;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16) + 128u * half;
+    const float* b2h = s_b2 + 128 * half;
+    const float* wah = s_wa + 128 * half;
+    float carry = 0.f;
     int cur_recv = -1;
     const float ba = GCL ? p.ba[0] : 0.f;
     auto flush = [&]() {
       if (cur_recv < 0) return;
-      if (GCL) {
-        float2 o;
-        o.x = carry0 / p.norm_div;
-        o.y = carry1 / p.norm_div;
-        *reinterpret_cast<float2*>(p.out + (int64_t)cur_recv * H + 2 * etid) = o;
-      } else if (etid < 3) {
-        p.out[(int64_t)cur_recv * 3 + etid] = p.x[(int64_t)cur_recv * 3 + etid] + carry0 / p.norm_div;
-      }
+      if (GCL) p.out[(int64_t)cur_recv * H + etid] = carry / p.norm_div;
+      else if (etid < 3) p.out[(int64_t)cur_recv * 3 + etid] = p.x[(int64_t)cur_recv * 3 + etid] + carry / p.norm_div;
     };
     for (int t = 0; t < ntiles; ++t) {
       const int as = t & 1;
-      const RowMeta* meta = s_meta + (t % META_BUFS) * TILE_M;
       ptx::mbar_wait(bar_accf(as), (t >> 1) & 1);
       ptx::tc_fence_after();
-      const RowMeta mine = meta[32 * q + lane];
+      const EMeta mine = s_emeta[(t % EMETA_BUFS) * TILE_M + 32 * q + lane];
       const bool live = (mine.flags & 3) == 1;   // real, off-diagonal edge
       const uint32_t acc = lane_base + 256u * as;
       float v[32];
       float dot = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
+      for (int cc = 0; cc < 4; ++cc) {
         ptx::tmem_ld32(acc + 32 * cc, v);
         ptx::tmem_wait_ld();
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_b2 + 32 * cc + 4 * k4);
-          const float4 ww = *reinterpret_cast<const float4*>(s_wa + 32 * cc + 4 * k4);
+          const float4 bb = *reinterpret_cast<const float4*>(b2h + 32 * cc + 4 * k4);
+          const float4 ww = *reinterpret_cast<const float4*>(wah + 32 * cc + 4 * k4);
           const float m0 = silu_edge<STRICT>(v[4 * k4 + 0] + bb.x), m1 = silu_edge<STRICT>(v[4 * k4 + 1] + bb.y);
           const float m2 = silu_edge<STRICT>(v[4 * k4 + 2] + bb.z), m3 = silu_edge<STRICT>(v[4 * k4 + 3] + bb.w);
           dot = fmaf(m0, ww.x, dot);
@@ -341,15 +364,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         }
         if (GCL) ptx::tmem_st32(acc + 32 * cc, v);
       }
+      // full-row dot product: exchange the two column halves
+      s_dot[half * TILE_M + 32 * q + lane] = dot;
+      ptx::named_bar_sync(4, EPI_THREADS);
+      dot = s_dot[32 * q + lane] + s_dot[TILE_M + 32 * q + lane];
       if (GCL) {
         ptx::tmem_wait_st();
         float att = 1.0f;
         if (p.attention) att = STRICT ? 1.0f / (1.0f + __expf(-(dot + ba))) : fmaf(0.5f, ptx::tanh_approx(0.5f * (dot + ba)), 0.5f);
         const float scale = live ? att : 0.f;
-        if (t > 0) ptx::named_bar_sync(2, 128);   // previous tile's combine has finished reading the scratch
+        if (t > 0) ptx::named_bar_sync(2, EPI_THREADS);   // previous tile's combine has finished reading the scratch
         const int c4 = (lane & 4) ? 16 : 0, c2 = (lane & 2) ? 8 : 0, c1 = (lane & 1) ? 4 : 0;
 #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
           ptx::tmem_ld32(acc + 32 * cc, v);
           ptx::tmem_wait_ld();
           float f[16], g[8], hsum[4];
@@ -374,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           }
           float4 o;
           o.x = hsum[0]; o.y = hsum[1]; o.z = hsum[2]; o.w = hsum[3];
-          *reinterpret_cast<float4*>(s_scr + (4 * q + (lane >> 3)) * H + 32 * cc + c4 + c2 + c1) = o;
+          *reinterpret_cast<float4*>(s_scr + (4 * q + (lane >> 3)) * H + 128 * half + 32 * cc + c4 + c2 + c1) = o;
         }
       } else {
         float tv = p.use_tanh ? (STRICT ? tanhf(dot) : ptx::tanh_approx(dot)) * p.range : dot;
@@ -386,39 +413,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           t1 += __shfl_xor_sync(0xffffffffu, t1, o);
           t2 += __shfl_xor_sync(0xffffffffu, t2, o);
         }
-        if (t > 0) ptx::named_bar_sync(2, 128);
-        if ((lane & 7) == 0) {
+        if (t > 0) ptx::named_bar_sync(2, EPI_THREADS);
+        if (half == 0 && (lane & 7) == 0) {
           float* dst = s_scr + (4 * q + (lane >> 3)) * H;
           dst[0] = t0; dst[1] = t1; dst[2] = t2;
         }
       }
-      // accumulator stage drained: hand it back to the MMA warp
       ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_acce(as), 0);
-        else ptx::mbar_arrive(bar_acce(as));
-      }
-      ptx::named_bar_sync(3, 128);   // scratch complete
-      // per-receiver running sums: groups of a tile are ordered by receiver
+      ptx::named_bar_sync(3, EPI_THREADS);   // scratch complete
+      // per-receiver running sums: groups of a tile are ordered by receiver; thread = output column
       if (GCL || etid < 3) {
 #pragma unroll 1
         for (int g = 0; g < 16; ++g) {
-          const int2 gi = s_grp[(t % GRP_BUFS) * 16 + g];
+          const int2 gi = s_grp[(t % EMETA_BUFS) * 16 + g];
           if (!gi.y) continue;                    // group outside this CTA's range
           if (gi.x != cur_recv) {
             flush();
             cur_recv = gi.x;
-            carry0 = carry1 = 0.f;
+            carry = 0.f;
           }
-          if (GCL) {
-            const float2 s2 = *reinterpret_cast<const float2*>(s_scr + g * H + 2 * etid);
-            carry0 += s2.x;
-            carry1 += s2.y;
-          } else {
-            carry0 += s_scr[g * H + etid];
-          }
+          carry += s_scr[g * H + etid];
         }
+      }
+      // accumulator stage drained and this tile's group table no longer needed: hand both back (the producers
+      // recycle the group-table slot of tile t when they prepare tile t+4, which the MMA warp gates on this arrive)
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_acce(as), 0);
+        else ptx::mbar_arrive(bar_acce(as));
       }
     }
     flush();
@@ -494,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   // ---- teardown ----------------------------------------------------------------------------------
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
-  if (warp == 8) ptx::tmem_dealloc<CG>(tmem, 512);
+  if (warp == MMA_WARP) ptx::tmem_dealloc<CG>(tmem, 512);
 }
 
 __global__ void plan_k(const int32_t* __restrict__ sizes, int B, int32_t* __restrict__ row_off) {
@@ -570,7 +592,9 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   int rc = ensure_plan(c);
   if (rc) return rc;
   tc::Params p{};
-  p.ab = reinterpret_cast<const float*>(c.ws + c.W.ab);
+  p.a_img = reinterpret_cast<const float*>(c.ws + c.W.ab);
+  p.kc_stride = (int64_t)c.B * c.N * 16;
+  p.b_img = p.a_img + (H / 16) * p.kc_stride;
   p.x = x;
   p.x0 = x0;
   p.sizes = c.sizes;
@@ -606,7 +630,7 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
 static int preproject(const FwdCtx& c, const SubLayer& S, const float* h, bool strict) {
   float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
   return linear_tc(c, h, H, H, nullptr, 0, 0, c.packed + S.w1ab_hi, c.packed + S.w1ab_lo, 2 * H, 128,
-                   reinterpret_cast<const float*>(c.packed + S.b1), ab, 2 * H, 0, nullptr, strict);
+                   reinterpret_cast<const float*>(c.packed + S.b1), ab, 2 * H, 3, nullptr, strict);
 }
 
 int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine) {
