@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
     auto publish = [&](int s) {
       ptx::fence_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_full(s));
+      if (lane == 0) ptx::mbar_arrive_relaxed(bar_full(s));
     };
     // four chunks of loads in flight per thread (the whole ring)
     float4 v0[8], v1[8], v2[8], v3[8];

@@ -31,6 +31,21 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive WITHOUT release semantics, for operand producers: a .release arrive compiles to MEMBAR.ALL.CTA, which also
+// waits for every global load the warp has in flight - i.e. it drains the software prefetch at every stage hand-off.
+// Ordering of the operand stores is provided explicitly instead: every lane runs fence.proxy.async after its
+// shared-memory stores (generic -> async proxy), __syncwarp orders the lanes, then one lane arrives.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of this cluster
 // (default .release.cta semantics, as CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release makes ptxas
 // emit MEMBAR.ALL.GPU + CCTL.IVALL, i.e. an L1 flush per arrive; the consumer of the data published here is the

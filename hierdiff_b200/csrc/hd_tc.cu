@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         ptx::fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_full(s), 0);
-          else ptx::mbar_arrive(bar_full(s));
+          if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster_relaxed(bar_full(s), 0);
+          else ptx::mbar_arrive_relaxed(bar_full(s));
         }
       };
       load_half(v0, 0);
