@@ -25,6 +25,16 @@ namespace hd {
 
 namespace tc {
 
+// per-role cycle accounting for scripts/edge_timing.cu (compiled out of the library)
+#ifdef HD_PHASE_TIMING
+__device__ long long g_acc[3][16];
+#define HD_T0() long long _t0 = clock64()
+#define HD_ACC(role, slot, cond) do { long long _t1 = clock64(); if ((cond) && blockIdx.x == 10) g_acc[role][slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define HD_T0() do { } while (0)
+#define HD_ACC(role, slot, cond) do { } while (0)
+#endif
+
 constexpr int TILE_M = 128;           // edge rows per CTA tile
 constexpr int KCH = 32;               // K columns per operand stage
 constexpr int NCH = H / KCH;          // 8 stages per tile
@@ -39,7 +49,7 @@ constexpr int MAX_B = 255;            // molecules per launch (row_off table in 
 constexpr int NPW = 8;                // producer warps
 constexpr int NEW = 8;                // epilogue warps
 constexpr int PROD_THREADS = 32 * NPW, EPI_THREADS = 32 * NEW;
-constexpr int NTHREADS = PROD_THREADS + EPI_THREADS + 32;   // + 1 MMA/alloc warp
+constexpr int NTHREADS = PROD_THREADS + EPI_THREADS + 64;   // + MMA/alloc warp + metadata warp
 
 struct PMeta {        // what the operand producers need of an edge row
   float r, d0;        // |x_i-x_j|^2, |x0_i-x0_j|^2
@@ -81,8 +91,8 @@ struct Smem {
   static constexpr int OFF_GRP = OFF_EMETA + EMETA_BUFS * TILE_M * (int)sizeof(EMeta);   // int2 [EMETA_BUFS][16]
   static constexpr int OFF_DOT = OFF_GRP + EMETA_BUFS * 16 * 8;    // [2][TILE_M] partial attention dots
   static constexpr int OFF_BAR = OFF_DOT + 2 * TILE_M * 4;
-  // barriers: full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2], w_local, w_ready ; then tmem ptr
-  static constexpr int NBAR = 2 * NSTAGE + 6;
+  // barriers: full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2], w_local, w_ready, meta, tile_start ; then tmem ptr
+  static constexpr int NBAR = 2 * NSTAGE + 8;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
@@ -144,7 +154,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   auto bar_accf = [&](int a) { return bar0 + 8u * (2 * NSTAGE + a); };
   auto bar_acce = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
   const uint32_t bar_wl = bar0 + 8u * (2 * NSTAGE + 4), bar_wr = bar0 + 8u * (2 * NSTAGE + 5);
-  constexpr int MMA_WARP = NPW + NEW;
+  const uint32_t bar_meta = bar0 + 8u * (2 * NSTAGE + 6), bar_tstart = bar0 + 8u * (2 * NSTAGE + 7);
+  constexpr int MMA_WARP = NPW + NEW, META_WARP = MMA_WARP + 1;
 
   // ---- one-time setup --------------------------------------------------------------------------
   for (int k = tid; k < H; k += NTHREADS) {
@@ -164,6 +175,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       ptx::mbar_init(bar_acce(a), NEW * CG);   // one elected arrive per epilogue warp of each CTA
     }
     ptx::mbar_init(bar_wl, 1);
+    ptx::mbar_init(bar_meta, 1);
+    ptx::mbar_init(bar_tstart, NPW);
     ptx::mbar_init(bar_wr, CG);
     ptx::fence_mbar_init();
   }
@@ -195,70 +208,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     // warp w builds rows [16w, 16w+16) of every operand stage: lane -> (row in 8-group, 4 columns of a 16-column half)
     const int rsub = (lane >> 1) & 7;
     const int qsub = 2 * (lane >> 4) + (lane & 1);
-    // metadata of tile row `tid` of tile t (threads 0..127), one tile ahead of its use
-    auto make_meta = [&](int t) {
-      const int R = row_begin + t * TILE_M + tid;
-      PMeta m;
-      EMeta e;
-      m.r = m.d0 = e.cd0 = e.cd1 = e.cd2 = 0.f;
-      m.recv = m.send = 0;
-      e.flags = 0;
-      if (R < row_end) {
-        const int b = find_mol(s_row, p.B, R);
-        const int n = p.sizes[b], npad = (n + 7) & ~7;
-        const int local = R - s_row[b];
-        const int i = local / npad, j = local - i * npad;
-        m.recv = b * p.N + i;
-        m.send = m.recv;
-        if (j < n) {
-          m.send = b * p.N + j;
-          e.flags = 1 | (j == i ? 2 : 0);
-          const float* xi = p.x + 3 * (int64_t)m.recv;
-          const float* xj = p.x + 3 * (int64_t)m.send;
-          const float* oi = p.x0 + 3 * (int64_t)m.recv;
-          const float* oj = p.x0 + 3 * (int64_t)m.send;
-          const float d0 = xi[0] - xj[0], d1 = xi[1] - xj[1], d2 = xi[2] - xj[2];
-          const float e0 = oi[0] - oj[0], e1 = oi[1] - oj[1], e2 = oi[2] - oj[2];
-          m.r = d0 * d0 + d1 * d1 + d2 * d2;
-          m.d0 = e0 * e0 + e1 * e1 + e2 * e2;
-          if (!GCL) {
-            const float nrm = sqrtf(m.r + 1e-8f) + p.norm_constant;
-            e.cd0 = d0 / nrm;
-            e.cd1 = d1 / nrm;
-            e.cd2 = d2 / nrm;
-          }
-        } else {
-          e.flags = 4;  // padding slot inside a real receiver's group (operand row = A_i + B_i: finite, masked later)
-        }
-      }
-      s_pmeta[(t % PMETA_BUFS) * TILE_M + tid] = m;
-      s_emeta[(t % EMETA_BUFS) * TILE_M + tid] = e;
-      if ((tid & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (tid >> 3)] = make_int2(m.recv, e.flags != 0);
-    };
-    if (tid < TILE_M && ntiles > 0) make_meta(0);
-    ptx::named_bar_sync(1, PROD_THREADS);
+    HD_T0();
     for (int t = 0; t < ntiles; ++t) {
+      ptx::mbar_wait(bar_meta, t & 1);    // row metadata of tile t (metadata warp)
       const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
-      // the 2 rows this thread feeds: 16*warp + 8*rb + rsub
+      // the 2 rows this thread feeds: 16*warp + 8*rb + rsub; a whole 8-row group is either live or not
       float rr[2], dd[2];
-      const float* pa[2];
-      const float* pb[2];
+      uint32_t oa[2], ob[2];
+      bool ok[2];
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
         const PMeta m = meta[16 * warp + 8 * rb + rsub];
         rr[rb] = m.r;
         dd[rb] = m.d0;
-        pa[rb] = p.a_img + (int64_t)m.recv * 16 + 4 * qsub;
-        pb[rb] = p.b_img + (int64_t)m.send * 16 + 4 * qsub;
+        ok[rb] = m.recv >= 0;
+        oa[rb] = (ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
+        ob[rb] = (ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub;
       }
-      // software pipeline over half stages (16 K-columns), loads issued 3 half stages ahead of their use
-      float4 v0[4], v1[4], v2[4], v3[4];   // {A row0, A row1, B row0, B row1}
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tstart);   // metadata slot of tile t-1 may be recycled
+      // software pipeline over half stages (16 K-columns): the loads of the next half stage are in flight while
+      // the current one is computed
+      float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1}
       auto load_half = [&](float4 (&v)[4], int hs) {
-        const int64_t o = hs * p.kc_stride;
+        const float* pa = p.a_img + hs * p.kc_stride;
+        const float* pb = p.b_img + hs * p.kc_stride;
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
-          v[rb] = __ldg(reinterpret_cast<const float4*>(pa[rb] + o));
-          v[2 + rb] = __ldg(reinterpret_cast<const float4*>(pb[rb] + o));
+          if (ok[rb]) {
+            v[rb] = __ldg(reinterpret_cast<const float4*>(pa + oa[rb]));
+            v[2 + rb] = __ldg(reinterpret_cast<const float4*>(pb + ob[rb]));
+          }
         }
       };
       auto half_step = [&](const float4 (&v)[4], int hs, int s) {
@@ -269,11 +249,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8;
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
+          if (!ok[rb]) continue;   // rows outside this CTA's range keep stale operand data; their accumulator
+                                   // rows are never read (group table)
           const float4 a = v[rb], b = v[2 + rb];
+#ifdef HD_EXP_NO_PROD_SILU
+          const float m0 = fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x));
+          const float m1 = fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y));
+          const float m2 = fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z));
+          const float m3 = fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w));
+#else
           const float m0 = silu_edge<STRICT>(fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x)));
           const float m1 = silu_edge<STRICT>(fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y)));
           const float m2 = silu_edge<STRICT>(fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z)));
           const float m3 = silu_edge<STRICT>(fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w)));
+#endif
           const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
           uint2 hi;
           hi.x = *reinterpret_cast<const uint32_t*>(&h01);
@@ -299,28 +288,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           else ptx::mbar_arrive_relaxed(bar_full(s));
         }
       };
-      load_half(v0, 0);
-      load_half(v1, 1);
-      load_half(v2, 2);
-      // next tile's row metadata while the first loads are in flight
-      if (tid < TILE_M && t + 1 < ntiles) make_meta(t + 1);
+      load_half(va, 0);
+      HD_ACC(0, 0, tid == 0);   // tile prologue
 #pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
-        const int gc = t * NCH + c, sa = gc % NSTAGE, sb = (gc + 1) % NSTAGE;
-        load_half(v3, 2 * c + 3);
-        ptx::mbar_wait(bar_empty(sa), ((gc / NSTAGE) & 1) ^ 1);
-        half_step(v0, 2 * c, sa);
-        if (c + 2 < NCH) load_half(v0, 2 * c + 4);
-        half_step(v1, 2 * c + 1, sa);
-        publish(sa);
-        if (c + 2 < NCH) load_half(v1, 2 * c + 5);
-        ptx::mbar_wait(bar_empty(sb), (((gc + 1) / NSTAGE) & 1) ^ 1);
-        half_step(v2, 2 * c + 2, sb);
-        if (c + 2 < NCH) load_half(v2, 2 * c + 6);
-        half_step(v3, 2 * c + 3, sb);
-        publish(sb);
+      for (int c = 0; c < NCH; ++c) {
+        const int gc = t * NCH + c, st = gc % NSTAGE;
+        load_half(vb, 2 * c + 1);
+        ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
+        HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
+        half_step(va, 2 * c, st);
+        if (c + 1 < NCH) load_half(va, 2 * c + 2);
+        half_step(vb, 2 * c + 1, st);
+        HD_ACC(0, 2, tid == 0);   // two half steps
+        publish(st);
+        HD_ACC(0, 3, tid == 0);   // publish
       }
-      ptx::named_bar_sync(1, PROD_THREADS);   // metadata of tile t+1 complete (and tile t's no longer read)
     }
   } else if (warp < MMA_WARP) {
     // =========================== epilogue ===========================
@@ -337,25 +319,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       if (GCL) p.out[(int64_t)cur_recv * H + etid] = carry / p.norm_div;
       else if (etid < 3) p.out[(int64_t)cur_recv * 3 + etid] = p.x[(int64_t)cur_recv * 3 + etid] + carry / p.norm_div;
     };
+    HD_T0();
     for (int t = 0; t < ntiles; ++t) {
       const int as = t & 1;
       ptx::mbar_wait(bar_accf(as), (t >> 1) & 1);
       ptx::tc_fence_after();
+      HD_ACC(1, 0, etid == 0);   // wait for the accumulator
       const EMeta mine = s_emeta[(t % EMETA_BUFS) * TILE_M + 32 * q + lane];
       const bool live = (mine.flags & 3) == 1;   // real, off-diagonal edge
+      const bool warp_live = __any_sync(0xffffffffu, mine.flags != 0);   // any row of this lane quarter in range
       const uint32_t acc = lane_base + 256u * as;
       float v[32];
       float dot = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < (warp_live ? 4 : 0); ++cc) {
         ptx::tmem_ld32(acc + 32 * cc, v);
         ptx::tmem_wait_ld();
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           const float4 bb = *reinterpret_cast<const float4*>(b2h + 32 * cc + 4 * k4);
           const float4 ww = *reinterpret_cast<const float4*>(wah + 32 * cc + 4 * k4);
+#ifdef HD_EXP_NO_EPI_SILU
+          const float m0 = v[4 * k4 + 0] + bb.x, m1 = v[4 * k4 + 1] + bb.y, m2 = v[4 * k4 + 2] + bb.z, m3 = v[4 * k4 + 3] + bb.w;
+#else
           const float m0 = silu_edge<STRICT>(v[4 * k4 + 0] + bb.x), m1 = silu_edge<STRICT>(v[4 * k4 + 1] + bb.y);
           const float m2 = silu_edge<STRICT>(v[4 * k4 + 2] + bb.z), m3 = silu_edge<STRICT>(v[4 * k4 + 3] + bb.w);
+#endif
           dot = fmaf(m0, ww.x, dot);
           dot = fmaf(m1, ww.y, dot);
           dot = fmaf(m2, ww.z, dot);
@@ -364,9 +353,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         }
         if (GCL) ptx::tmem_st32(acc + 32 * cc, v);
       }
+      HD_ACC(1, 1, etid == 0);   // pass 1
       // full-row dot product: exchange the two column halves
       s_dot[half * TILE_M + 32 * q + lane] = dot;
       ptx::named_bar_sync(4, EPI_THREADS);
+      HD_ACC(1, 2, etid == 0);   // exchange barrier
       dot = s_dot[32 * q + lane] + s_dot[TILE_M + 32 * q + lane];
       if (GCL) {
         ptx::tmem_wait_st();
@@ -376,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         if (t > 0) ptx::named_bar_sync(2, EPI_THREADS);   // previous tile's combine has finished reading the scratch
         const int c4 = (lane & 4) ? 16 : 0, c2 = (lane & 2) ? 8 : 0, c1 = (lane & 1) ? 4 : 0;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < (warp_live ? 4 : 0); ++cc) {
           ptx::tmem_ld32(acc + 32 * cc, v);
           ptx::tmem_wait_ld();
           float f[16], g[8], hsum[4];
@@ -419,31 +410,88 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           dst[0] = t0; dst[1] = t1; dst[2] = t2;
         }
       }
+      HD_ACC(1, 3, etid == 0);   // pass 2 (incl. waiting for the previous combine)
       ptx::tc_fence_before();
       ptx::named_bar_sync(3, EPI_THREADS);   // scratch complete
+      HD_ACC(1, 4, etid == 0);   // scratch barrier
       // per-receiver running sums: groups of a tile are ordered by receiver; thread = output column
       if (GCL || etid < 3) {
-#pragma unroll 1
+        int2 gi[16];
+        float sv[16];
+#pragma unroll
         for (int g = 0; g < 16; ++g) {
-          const int2 gi = s_grp[(t % EMETA_BUFS) * 16 + g];
-          if (!gi.y) continue;                    // group outside this CTA's range
-          if (gi.x != cur_recv) {
+          gi[g] = s_grp[(t % EMETA_BUFS) * 16 + g];
+          sv[g] = s_scr[g * H + etid];
+        }
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          if (!gi[g].y) continue;                 // group outside this CTA's range
+          if (gi[g].x != cur_recv) {
             flush();
-            cur_recv = gi.x;
+            cur_recv = gi[g].x;
             carry = 0.f;
           }
-          carry += s_scr[g * H + etid];
+          carry += sv[g];
         }
       }
       // accumulator stage drained and this tile's group table no longer needed: hand both back (the producers
       // recycle the group-table slot of tile t when they prepare tile t+4, which the MMA warp gates on this arrive)
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_acce(as), 0);
-        else ptx::mbar_arrive(bar_acce(as));
+        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster_relaxed(bar_acce(as), 0);
+        else ptx::mbar_arrive_relaxed(bar_acce(as));
       }
+      HD_ACC(1, 5, etid == 0);   // combine + release
     }
     flush();
+  } else if (warp == META_WARP) {
+    // =========================== row metadata ===========================
+    // one warp prepares the per-row metadata of tile t+1 while the producers work on tile t
+    for (int t = 0; t < ntiles; ++t) {
+      if (t > 0) ptx::mbar_wait(bar_tstart, (t - 1) & 1);   // producers hold tile t-1's metadata in registers
+      for (int rq = 0; rq < TILE_M / 32; ++rq) {
+        const int row = 32 * rq + lane;
+        const int R = row_begin + t * TILE_M + row;
+        PMeta m;
+        EMeta e;
+        m.r = m.d0 = e.cd0 = e.cd1 = e.cd2 = 0.f;
+        m.recv = m.send = -1;    // row outside this CTA's range
+        e.flags = 0;
+        if (R < row_end) {
+          const int b = find_mol(s_row, p.B, R);
+          const int n = p.sizes[b], npad = (n + 7) & ~7;
+          const int local = R - s_row[b];
+          const int i = local / npad, j = local - i * npad;
+          m.recv = b * p.N + i;
+          m.send = m.recv;
+          if (j < n) {
+            m.send = b * p.N + j;
+            e.flags = 1 | (j == i ? 2 : 0);
+            const float* xi = p.x + 3 * (int64_t)m.recv;
+            const float* xj = p.x + 3 * (int64_t)m.send;
+            const float* oi = p.x0 + 3 * (int64_t)m.recv;
+            const float* oj = p.x0 + 3 * (int64_t)m.send;
+            const float d0 = xi[0] - xj[0], d1 = xi[1] - xj[1], d2 = xi[2] - xj[2];
+            const float e0 = oi[0] - oj[0], e1 = oi[1] - oj[1], e2 = oi[2] - oj[2];
+            m.r = d0 * d0 + d1 * d1 + d2 * d2;
+            m.d0 = e0 * e0 + e1 * e1 + e2 * e2;
+            if (!GCL) {
+              const float nrm = sqrtf(m.r + 1e-8f) + p.norm_constant;
+              e.cd0 = d0 / nrm;
+              e.cd1 = d1 / nrm;
+              e.cd2 = d2 / nrm;
+            }
+          } else {
+            e.flags = 4;  // padding slot inside a real receiver's group (operand row = A_i + B_i: finite, masked later)
+          }
+        }
+        s_pmeta[(t % PMETA_BUFS) * TILE_M + row] = m;
+        s_emeta[(t % EMETA_BUFS) * TILE_M + row] = e;
+        if ((row & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (row >> 3)] = make_int2(m.recv, e.flags != 0);
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_meta);
+    }
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -465,14 +513,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       if (rank == 0) {
         ptx::mbar_wait(bar_wr, 0);
         constexpr uint32_t IDESC = CG == 2 ? ptx::idesc_bf16(256, 256) : ptx::idesc_bf16(128, 128);
+        HD_T0();
         for (int t = 0; t < ntiles; ++t) {
           const int as = t & 1;
           ptx::mbar_wait(bar_acce(as), ((t >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
+          HD_ACC(2, 0, true);   // wait for a free accumulator
           for (int c = 0; c < NCH; ++c) {
             const int gc = t * NCH + c, s = gc % NSTAGE;
             ptx::mbar_wait(bar_full(s), (gc / NSTAGE) & 1);
             ptx::tc_fence_after();
+            HD_ACC(2, 1, true);   // wait for operands
             const uint32_t a_hi = sbase + S::OFF_A + s * S::STAGE;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
@@ -505,6 +556,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
               }
             }
             ptx::mma_commit<CG>(bar_empty(s));     // operand stage consumed (both CTAs)
+            HD_ACC(2, 2, true);   // issue
           }
           ptx::mma_commit<CG>(bar_accf(as));       // accumulator complete (both CTAs)
         }
