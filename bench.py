@@ -285,9 +285,17 @@ def edge_kernel_roofline(model, loop, engine, B, N, iters=20):
     else:
         peak = float(peaks.get("bf16_tflops", 1590.0))
         peak_name = f"bf16 dense burst, {src} (kernel timed alone)"
+    traffic = None     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", f"r1_edge_{engine}_metrics.json")) as f:
+            m = json.load(f)["launches"][0]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(m[k]["value"]) * unit[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except (OSError, KeyError, ValueError, IndexError):
+        pass
     achieved = flops / (ms * 1e-3) / 1e12
     return {"kernel": "fused GCL edge kernel (block 0, gcl_0)", "bound": "tensor", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_name,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_name,
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "tensor_passes": {"strict": 3, "fast": 1, "fp32": 0}[engine],
             "hbm_GBps_algorithmic": hbm_bytes / (ms * 1e-3) / 1e9,

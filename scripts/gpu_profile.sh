@@ -1,10 +1,10 @@
 #!/bin/bash
-# ncu evidence for profiles/: (1) launch list of one eager reverse-step loop, (2) --set full captures of the
-# dominant kernels at the C2 shape.  usage: bash scripts/gpu_profile.sh <engine> <tag>
+# ncu evidence for profiles/ (B200_PROFILING.md recipe): (1) launch list of a short eager chain, (2) --set full
+# captures of the two dominant kernels at the C2 shape.  usage: bash scripts/gpu_profile.sh <engine> <tag>
 E=${1:-strict}; TAG=${2:-r1}
 mkdir -p gpurun_out
 echo "== ncu launch list ($E)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 0 -c 2500 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
   --log-file gpurun_out/launches_${E}_${TAG}.csv \
   python bench.py --engine $E --steps 1 --warmup 1 --no-cpu-baseline --steps-per-graph 1 --no-graph --timesteps 12 \
   > gpurun_out/ncu_bench_${E}.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/ncu_bench_${E}.log | cut -c1-200
