@@ -27,12 +27,15 @@ namespace tc {
 
 // per-role cycle accounting for scripts/edge_timing.cu (compiled out of the library)
 #ifdef HD_PHASE_TIMING
-__device__ long long g_acc[3][16];
-#define HD_T0() long long _t0 = clock64()
-#define HD_ACC(role, slot, cond) do { long long _t1 = clock64(); if ((cond) && blockIdx.x == 10) g_acc[role][slot] += _t1 - _t0; _t0 = _t1; } while (0)
+__device__ long long g_acc[2][3][16];   // [CTA 10 | CTA 11][role][slot]
+// accumulate in registers (a global read-modify-write per stamp would stall the warp ~350 cycles), flush once
+#define HD_T0() long long _t0 = clock64(); long long _acc[6] = {0, 0, 0, 0, 0, 0}
+#define HD_ACC(role, slot, cond) do { long long _t1 = clock64(); _acc[slot] += _t1 - _t0; _t0 = _t1; } while (0)
+#define HD_FLUSH(role, cond) do { if ((cond) && (blockIdx.x >> 1) == 5) for (int _i = 0; _i < 6; ++_i) g_acc[blockIdx.x & 1][role][_i] += _acc[_i]; } while (0)
 #else
 #define HD_T0() do { } while (0)
 #define HD_ACC(role, slot, cond) do { } while (0)
+#define HD_FLUSH(role, cond) do { } while (0)
 #endif
 
 constexpr int TILE_M = 128;           // edge rows per CTA tile
@@ -230,45 +233,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       // software pipeline over half stages (16 K-columns): the loads of the next half stage are in flight while
       // the current one is computed
       float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1}
+#pragma unroll
+      for (int k = 0; k < 4; ++k) va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       auto load_half = [&](float4 (&v)[4], int hs) {
         const float* pa = p.a_img + hs * p.kc_stride;
         const float* pb = p.b_img + hs * p.kc_stride;
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
+#ifndef HD_EXP_NO_LDG
           if (ok[rb]) {
             v[rb] = __ldg(reinterpret_cast<const float4*>(pa + oa[rb]));
             v[2 + rb] = __ldg(reinterpret_cast<const float4*>(pb + ob[rb]));
           }
+#endif
         }
       };
+      // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
+      // MUFU latencies of the chains overlap
       auto half_step = [&](const float4 (&v)[4], int hs, int s) {
         const int ph = hs & 1;
         const int k0 = 16 * hs + 4 * qsub;
         const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
         const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
-        uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8;
+        uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8 +
+                         (16 * warp + rsub) * 16;
+        if (!(ok[0] || ok[1])) return;   // rows outside this CTA's range keep stale operand data; their
+                                         // accumulator rows are never read (group table)
+        float pre[8], m[8];
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
-          if (!ok[rb]) continue;   // rows outside this CTA's range keep stale operand data; their accumulator
-                                   // rows are never read (group table)
           const float4 a = v[rb], b = v[2 + rb];
+          pre[4 * rb + 0] = fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x));
+          pre[4 * rb + 1] = fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y));
+          pre[4 * rb + 2] = fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z));
+          pre[4 * rb + 3] = fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w));
+        }
 #ifdef HD_EXP_NO_PROD_SILU
-          const float m0 = fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x));
-          const float m1 = fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y));
-          const float m2 = fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z));
-          const float m3 = fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = pre[k];
 #else
-          const float m0 = silu_edge<STRICT>(fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x)));
-          const float m1 = silu_edge<STRICT>(fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y)));
-          const float m2 = silu_edge<STRICT>(fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z)));
-          const float m3 = silu_edge<STRICT>(fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w)));
+        if constexpr (STRICT) {
+          float e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(-1.4426950408889634f * pre[k]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) e[k] = ptx::rcp_approx(1.0f + e[k]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];
+        } else {
+          float th[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(0.5f * pre[k]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = fmaf(0.5f * pre[k], th[k], 0.5f * pre[k]);
+        }
 #endif
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          if (!ok[rb]) continue;
+          const float m0 = m[4 * rb], m1 = m[4 * rb + 1], m2 = m[4 * rb + 2], m3 = m[4 * rb + 3];
           const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
           uint2 hi;
           hi.x = *reinterpret_cast<const uint32_t*>(&h01);
           hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-          uint8_t* dst = stage + (16 * warp + 8 * rb + rsub) * 16;
+          uint8_t* dst = stage + 8 * rb * 16;
           *reinterpret_cast<uint2*>(dst) = hi;
+#ifndef HD_EXP_NO_LO
           if constexpr (STRICT) {
             const float l0 = m0 - __uint_as_float(hi.x << 16), l1 = m1 - __uint_as_float(hi.x & 0xffff0000u);
             const float l2 = m2 - __uint_as_float(hi.y << 16), l3 = m3 - __uint_as_float(hi.y & 0xffff0000u);
@@ -278,6 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
             lo.y = *reinterpret_cast<const uint32_t*>(&g23);
             *reinterpret_cast<uint2*>(dst + A_HALF) = lo;
           }
+#endif
         }
       };
       auto publish = [&](int s) {
@@ -294,6 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       for (int c = 0; c < NCH; ++c) {
         const int gc = t * NCH + c, st = gc % NSTAGE;
         load_half(vb, 2 * c + 1);
+        HD_ACC(0, 5, tid == 0);   // issue the next half stage's loads
         ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
         HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
         half_step(va, 2 * c, st);
@@ -304,6 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         HD_ACC(0, 3, tid == 0);   // publish
       }
     }
+    HD_FLUSH(0, tid == 0);
   } else if (warp < MMA_WARP) {
     // =========================== epilogue ===========================
     // warp -> TMEM lane quarter q (= warp % 4) and column half; thread = edge row, 128 of the 256 columns
@@ -367,7 +400,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         if (t > 0) ptx::named_bar_sync(2, EPI_THREADS);   // previous tile's combine has finished reading the scratch
         const int c4 = (lane & 4) ? 16 : 0, c2 = (lane & 2) ? 8 : 0, c1 = (lane & 1) ? 4 : 0;
 #pragma unroll 1
+#ifdef HD_EXP_NO_PASS2
+        for (int cc = 0; cc < 0; ++cc) {
+#else
         for (int cc = 0; cc < (warp_live ? 4 : 0); ++cc) {
+#endif
           ptx::tmem_ld32(acc + 32 * cc, v);
           ptx::tmem_wait_ld();
           float f[16], g[8], hsum[4];
@@ -444,6 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       HD_ACC(1, 5, etid == 0);   // combine + release
     }
     flush();
+    HD_FLUSH(1, etid == 0);
   } else if (warp == META_WARP) {
     // =========================== row metadata ===========================
     // one warp prepares the per-row metadata of tile t+1 while the producers work on tile t
@@ -560,6 +598,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           }
           ptx::mma_commit<CG>(bar_accf(as));       // accumulator complete (both CTAs)
         }
+        HD_FLUSH(2, true);
       }
     }
     __syncwarp();

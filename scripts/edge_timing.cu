@@ -15,7 +15,7 @@ int linear_tc(const FwdCtx&, const float*, int, int, const float*, int, int, con
 template <bool GCL, bool STRICT>
 static void run(const char* name, hd::tc::Params p) {
   using namespace hd;
-  long long zero[3][16] = {};
+  long long zero[2][3][16] = {};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0;
@@ -27,19 +27,23 @@ static void run(const char* name, hd::tc::Params p) {
     cudaDeviceSynchronize();
     cudaEventElapsedTime(&ms, e0, e1);
   }
-  long long acc[3][16];
-  cudaMemcpyFromSymbol(acc, tc::g_acc, sizeof(acc));
-  printf("%s: %.2f us/launch; err=%s  (cycles per launch, CTA 10)\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
-  const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier"};
+  long long acc2[2][3][16];
+  cudaMemcpyFromSymbol(acc2, tc::g_acc, sizeof(acc2));
+  for (int cta = 0; cta < 2; ++cta) {
+  long long (*acc)[16] = acc2[cta];
+  printf(" -- CTA %d (cluster rank %d)\n", 10 + cta, cta);
+  printf("%s: %.2f us/launch; err=%s  (cycles per launch)\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
+  const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier", "issue loads"};
   const char* en[] = {"wait accumulator", "pass 1", "dot exchange", "pass 2", "scratch barrier", "combine+release"};
   const char* mn[] = {"wait free acc", "wait operands", "issue"};
   long long s = 0;
-  for (int i = 0; i < 5; ++i) { printf("  producer  %-20s %8lld\n", pn[i], acc[0][i] / 10); s += acc[0][i] / 10; }
+  for (int i = 0; i < 6; ++i) { printf("  producer  %-20s %8lld\n", pn[i], acc[0][i] / 10); s += acc[0][i] / 10; }
   printf("  producer  total %lld\n", s); s = 0;
   for (int i = 0; i < 6; ++i) { printf("  epilogue  %-20s %8lld\n", en[i], acc[1][i] / 10); s += acc[1][i] / 10; }
   printf("  epilogue  total %lld\n", s); s = 0;
   for (int i = 0; i < 3; ++i) { printf("  mma       %-20s %8lld\n", mn[i], acc[2][i] / 10); s += acc[2][i] / 10; }
   printf("  mma       total %lld\n", s);
+  }
 }
 
 int main() {
