@@ -211,131 +211,158 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     // warp w builds rows [16w, 16w+16) of every operand stage: lane -> (row in 8-group, 4 columns of a 16-column half)
     const int rsub = (lane >> 1) & 7;
     const int qsub = 2 * (lane >> 4) + (lane & 1);
-    HD_T0();
-    for (int t = 0; t < ntiles; ++t) {
-      ptx::mbar_wait(bar_meta, t & 1);    // row metadata of tile t (metadata warp)
-      const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
-      // the 2 rows this thread feeds: 16*warp + 8*rb + rsub; a whole 8-row group is either live or not
+    const uint32_t kcs = (uint32_t)p.kc_stride;   // floats between 16-column chunks; b_img = a_img + 16 chunks
+    // per-tile state of the 2 rows this thread feeds (16*warp + 8*rb + rsub); an 8-row group is live or dead as a whole
+    struct RowState {
       float rr[2], dd[2];
-      uint32_t oa[2], ob[2];
+      uint32_t oa[2], ob[2];   // element offsets of A_i / B_j in chunk 0
       bool ok[2];
+    };
+    auto read_meta = [&](int t, RowState& r) {
+      const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
         const PMeta m = meta[16 * warp + 8 * rb + rsub];
-        rr[rb] = m.r;
-        dd[rb] = m.d0;
-        ok[rb] = m.recv >= 0;
-        oa[rb] = (ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
-        ob[rb] = (ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub;
+        r.rr[rb] = m.r;
+        r.dd[rb] = m.d0;
+        r.ok[rb] = m.recv >= 0;
+        r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
+        r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tstart);   // metadata slot of tile t-1 may be recycled
-      // software pipeline over half stages (16 K-columns): the loads of the next half stage are in flight while
-      // the current one is computed
-      float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1}
+    };
+    auto load_half = [&](float4 (&v)[4], const RowState& r, int hs) {
+      const uint32_t o = hs * kcs;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto load_half = [&](float4 (&v)[4], int hs) {
-        const float* pa = p.a_img + hs * p.kc_stride;
-        const float* pb = p.b_img + hs * p.kc_stride;
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
+      for (int rb = 0; rb < 2; ++rb) {
 #ifndef HD_EXP_NO_LDG
-          if (ok[rb]) {
-            v[rb] = __ldg(reinterpret_cast<const float4*>(pa + oa[rb]));
-            v[2 + rb] = __ldg(reinterpret_cast<const float4*>(pb + ob[rb]));
-          }
+        if (r.ok[rb]) {
+          v[rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[rb])));
+          v[2 + rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.ob[rb])));
+        }
 #endif
-        }
-      };
-      // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
-      // MUFU latencies of the chains overlap
-      auto half_step = [&](const float4 (&v)[4], int hs, int s) {
-        const int ph = hs & 1;
-        const int k0 = 16 * hs + 4 * qsub;
-        const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
-        const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
-        uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8 +
-                         (16 * warp + rsub) * 16;
-        if (!(ok[0] || ok[1])) return;   // rows outside this CTA's range keep stale operand data; their
-                                         // accumulator rows are never read (group table)
-        float pre[8], m[8];
+      }
+    };
+    // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
+    // MUFU latencies of the chains overlap
+    auto half_step = [&](const float4 (&v)[4], const RowState& r, int hs, int s) {
+      const int ph = hs & 1;
+      const int k0 = 16 * hs + 4 * qsub;
+      const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
+      const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
+      uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8 +
+                       (16 * warp + rsub) * 16;
+      if (!(r.ok[0] || r.ok[1])) return;   // rows outside this CTA's range keep stale operand data; their
+                                           // accumulator rows are never read (group table)
+      float pre[8], m[8];
 #pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
-          const float4 a = v[rb], b = v[2 + rb];
-          pre[4 * rb + 0] = fmaf(dd[rb], w_d.x, fmaf(rr[rb], w_r.x, a.x + b.x));
-          pre[4 * rb + 1] = fmaf(dd[rb], w_d.y, fmaf(rr[rb], w_r.y, a.y + b.y));
-          pre[4 * rb + 2] = fmaf(dd[rb], w_d.z, fmaf(rr[rb], w_r.z, a.z + b.z));
-          pre[4 * rb + 3] = fmaf(dd[rb], w_d.w, fmaf(rr[rb], w_r.w, a.w + b.w));
-        }
+      for (int rb = 0; rb < 2; ++rb) {
+        const float4 a = v[rb], b = v[2 + rb];
+        pre[4 * rb + 0] = fmaf(r.dd[rb], w_d.x, fmaf(r.rr[rb], w_r.x, a.x + b.x));
+        pre[4 * rb + 1] = fmaf(r.dd[rb], w_d.y, fmaf(r.rr[rb], w_r.y, a.y + b.y));
+        pre[4 * rb + 2] = fmaf(r.dd[rb], w_d.z, fmaf(r.rr[rb], w_r.z, a.z + b.z));
+        pre[4 * rb + 3] = fmaf(r.dd[rb], w_d.w, fmaf(r.rr[rb], w_r.w, a.w + b.w));
+      }
 #ifdef HD_EXP_NO_PROD_SILU
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = pre[k];
+      for (int k = 0; k < 8; ++k) m[k] = pre[k];
 #else
-        if constexpr (STRICT) {
-          float e[8];
+      if constexpr (STRICT) {
+        float e[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(-1.4426950408889634f * pre[k]);
+        for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(-1.4426950408889634f * pre[k]);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = ptx::rcp_approx(1.0f + e[k]);
+        for (int k = 0; k < 8; ++k) e[k] = ptx::rcp_approx(1.0f + e[k]);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];
-        } else {
-          float th[8];
+        for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];
+      } else {
+        float th[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(0.5f * pre[k]);
+        for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(0.5f * pre[k]);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) m[k] = fmaf(0.5f * pre[k], th[k], 0.5f * pre[k]);
-        }
+        for (int k = 0; k < 8; ++k) m[k] = fmaf(0.5f * pre[k], th[k], 0.5f * pre[k]);
+      }
 #endif
 #pragma unroll
-        for (int rb = 0; rb < 2; ++rb) {
-          if (!ok[rb]) continue;
-          const float m0 = m[4 * rb], m1 = m[4 * rb + 1], m2 = m[4 * rb + 2], m3 = m[4 * rb + 3];
-          const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
-          uint2 hi;
-          hi.x = *reinterpret_cast<const uint32_t*>(&h01);
-          hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-          uint8_t* dst = stage + 8 * rb * 16;
-          *reinterpret_cast<uint2*>(dst) = hi;
+      for (int rb = 0; rb < 2; ++rb) {
+        if (!r.ok[rb]) continue;
+        const float m0 = m[4 * rb], m1 = m[4 * rb + 1], m2 = m[4 * rb + 2], m3 = m[4 * rb + 3];
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
+        uint2 hi;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+        hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+        uint8_t* dst = stage + 8 * rb * 16;
+        *reinterpret_cast<uint2*>(dst) = hi;
 #ifndef HD_EXP_NO_LO
-          if constexpr (STRICT) {
-            const float l0 = m0 - __uint_as_float(hi.x << 16), l1 = m1 - __uint_as_float(hi.x & 0xffff0000u);
-            const float l2 = m2 - __uint_as_float(hi.y << 16), l3 = m3 - __uint_as_float(hi.y & 0xffff0000u);
-            const __nv_bfloat162 g01 = __floats2bfloat162_rn(l0, l1), g23 = __floats2bfloat162_rn(l2, l3);
-            uint2 lo;
-            lo.x = *reinterpret_cast<const uint32_t*>(&g01);
-            lo.y = *reinterpret_cast<const uint32_t*>(&g23);
-            *reinterpret_cast<uint2*>(dst + A_HALF) = lo;
-          }
+        if constexpr (STRICT) {
+          const float l0 = m0 - __uint_as_float(hi.x << 16), l1 = m1 - __uint_as_float(hi.x & 0xffff0000u);
+          const float l2 = m2 - __uint_as_float(hi.y << 16), l3 = m3 - __uint_as_float(hi.y & 0xffff0000u);
+          const __nv_bfloat162 g01 = __floats2bfloat162_rn(l0, l1), g23 = __floats2bfloat162_rn(l2, l3);
+          uint2 lo;
+          lo.x = *reinterpret_cast<const uint32_t*>(&g01);
+          lo.y = *reinterpret_cast<const uint32_t*>(&g23);
+          *reinterpret_cast<uint2*>(dst + A_HALF) = lo;
+        }
 #endif
-        }
-      };
-      auto publish = [&](int s) {
-        ptx::fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster_relaxed(bar_full(s), 0);
-          else ptx::mbar_arrive_relaxed(bar_full(s));
-        }
-      };
-      load_half(va, 0);
-      HD_ACC(0, 0, tid == 0);   // tile prologue
+      }
+    };
+    auto publish = [&](int s) {
+      ptx::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster_relaxed(bar_full(s), 0);
+        else ptx::mbar_arrive_relaxed(bar_full(s));
+      }
+    };
+    auto tile_started = [&]() {   // this warp holds the tile's metadata in registers: its slot may be recycled
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tstart);
+    };
+
+    HD_T0();
+    RowState cur, nxt;
+    float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1} of the two half stages in flight
+#pragma unroll
+    for (int k = 0; k < 4; ++k) va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ntiles > 0) {
+      ptx::mbar_wait(bar_meta, 0);
+      read_meta(0, cur);
+      tile_started();
+      load_half(va, cur, 0);
+    }
+    nxt = cur;
+    int pending = -1;   // operand stage written but not yet published (published one half step late, when the
+                        // fence no longer has to wait for its stores)
+    for (int t = 0; t < ntiles; ++t) {
+      HD_ACC(0, 0, tid == 0);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int gc = t * NCH + c, st = gc % NSTAGE;
-        load_half(vb, 2 * c + 1);
-        HD_ACC(0, 5, tid == 0);   // issue the next half stage's loads
+        load_half(vb, cur, 2 * c + 1);
+        HD_ACC(0, 5, tid == 0);   // issue loads
         ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
         HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
-        half_step(va, 2 * c, st);
-        if (c + 1 < NCH) load_half(va, 2 * c + 2);
-        half_step(vb, 2 * c + 1, st);
-        HD_ACC(0, 2, tid == 0);   // two half steps
-        publish(st);
+        half_step(va, cur, 2 * c, st);
+        HD_ACC(0, 2, tid == 0);   // half steps
+        if (pending >= 0) publish(pending);
         HD_ACC(0, 3, tid == 0);   // publish
+        if (c + 1 < NCH) {
+          load_half(va, cur, 2 * c + 2);
+        } else if (t + 1 < ntiles) {   // first operands of the next tile, so the tile boundary costs no load latency
+          ptx::mbar_wait(bar_meta, (t + 1) & 1);
+          read_meta(t + 1, nxt);
+          load_half(va, nxt, 0);
+        }
+        HD_ACC(0, 5, tid == 0);
+        half_step(vb, cur, 2 * c + 1, st);
+        HD_ACC(0, 2, tid == 0);
+        pending = st;
+      }
+      if (t + 1 < ntiles) {
+        cur = nxt;
+        tile_started();
       }
     }
+    if (pending >= 0) publish(pending);
     HD_FLUSH(0, tid == 0);
   } else if (warp < MMA_WARP) {
     // =========================== epilogue ===========================
