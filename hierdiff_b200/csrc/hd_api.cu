@@ -17,6 +17,8 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
 __global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t, const int32_t* __restrict__ sizes,
                        int B, int N, int F, float* __restrict__ hin, float* __restrict__ x, float* __restrict__ x0,
                        int32_t* __restrict__ nanflag) {
+  pdl_wait();
+  pdl_trigger();
   const int D = 3 + F, Fi = F + 1;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) *nanflag = 0;
@@ -41,6 +43,8 @@ __global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t,
 __global__ void __launch_bounds__(256) embed_k(const float* __restrict__ hin, int Fi, const float* __restrict__ wT,
                                                const float* __restrict__ bias, const int32_t* __restrict__ sizes,
                                                int N, float* __restrict__ h) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t r = blockIdx.x;
   const int c = threadIdx.x, b = (int)(r / N), i = (int)(r % N);
   float v = 0.f;
@@ -55,6 +59,8 @@ __global__ void __launch_bounds__(256) embed_k(const float* __restrict__ hin, in
 __global__ void __launch_bounds__(256) out_k(const float* __restrict__ h, const float* __restrict__ w,
                                              const float* __restrict__ bias, int Fi,
                                              const int32_t* __restrict__ sizes, int N, float* __restrict__ hout) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t r = blockIdx.x;
   const int b = (int)(r / N), i = (int)(r % N), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool real = i < sizes[b];
@@ -71,6 +77,8 @@ __global__ void __launch_bounds__(256) out_k(const float* __restrict__ h, const 
 __global__ void vel_k(const float* __restrict__ xf, const float* __restrict__ x0, const float* __restrict__ hout,
                       const int32_t* __restrict__ sizes, int B, int N, int F, float* __restrict__ eps_raw,
                       int32_t* __restrict__ nanflag) {
+  pdl_wait();
+  pdl_trigger();
   const int D = 3 + F, Fi = F + 1;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * N * D) return;
@@ -107,6 +115,8 @@ __device__ __forceinline__ void block_mean3(const float* v, int N, int D, int n,
 __global__ void __launch_bounds__(128) cog_k(const float* __restrict__ eps_raw, const int32_t* __restrict__ sizes,
                                              int N, int F, const int32_t* __restrict__ nanflag,
                                              float* __restrict__ eps, int32_t* __restrict__ flags) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sv[];  // [N][D]
   __shared__ float s_mean[3];
   const int D = 3 + F, b = blockIdx.x, n = sizes[b];
@@ -152,6 +162,8 @@ __device__ __forceinline__ void load_noise(const float* rx, const float* rh, int
 __global__ void __launch_bounds__(128) combine_noise_k(const float* __restrict__ rx, const float* __restrict__ rh,
                                                        const int32_t* __restrict__ sizes, int N, int F,
                                                        float* __restrict__ z) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float nz[];
   __shared__ float s_mean[3];
   const int D = 3 + F, b = blockIdx.x;
@@ -165,6 +177,8 @@ __global__ void __launch_bounds__(128) reverse_step_k(const float* __restrict__ 
                                                       const int32_t* __restrict__ sizes, int N, int F,
                                                       const float* __restrict__ sched, int sched_per_mol,
                                                       float* __restrict__ zs, int32_t* __restrict__ flags) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];  // nz [N*D], ev [N*D], zv [N*D]
   __shared__ float s_mean[3];
   __shared__ float s_chk[3];
@@ -229,6 +243,8 @@ __global__ void __launch_bounds__(128) final_decode_k(const float* __restrict__ 
                                                       const float* __restrict__ sched, int sched_per_mol,
                                                       float norm_x, float norm_h, float bias_h,
                                                       float* __restrict__ x, float* __restrict__ h) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float nz[];
   __shared__ float s_mean[3];
   const int D = 3 + F, b = blockIdx.x, n = sizes[b];
@@ -277,6 +293,8 @@ __global__ void final_scalars_k(const float* __restrict__ g0, int count, float* 
 
 __global__ void loop_fetch_k(int32_t* counter, const float* __restrict__ t_table, const float* __restrict__ sched_table,
                              int B, float* __restrict__ t_cur, float* __restrict__ sched_cur) {
+  pdl_wait();
+  pdl_trigger();
   const int k = *counter;
   for (int b = threadIdx.x; b < B; b += blockDim.x) t_cur[b] = t_table[k];
   if (threadIdx.x < 3) sched_cur[threadIdx.x] = sched_table[3 * k + threadIdx.x];
@@ -393,20 +411,24 @@ HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, con
   auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
   auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   int32_t* nanflag = reinterpret_cast<int32_t*>(c.ws + c.W.nanflag);
-  prep_k<<<(unsigned)((BN * (D + 1) + 255) / 256), 256, 0, c.stream>>>(z, t, sizes, B, N, F, WF(c.W.hin), WF(c.W.x),
-                                                                      WF(c.W.x0), nanflag);
-  HD_CHECK_LAUNCH();
-  embed_k<<<(unsigned)BN, 256, 0, c.stream>>>(WF(c.W.hin), Fi, PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h));
-  HD_CHECK_LAUNCH();
+  HD_CHECK_CUDA(launch_pdl(prep_k, dim3((unsigned)((BN * (D + 1) + 255) / 256)), dim3(256), 0, c.stream, z, t, sizes, B, N,
+                          F, WF(c.W.hin), WF(c.W.x), WF(c.W.x0), nanflag));
+  count_launch();
+  HD_CHECK_CUDA(launch_pdl(embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.hin), Fi,
+                          PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h)));
+  count_launch();
   float* xf = nullptr;
   if ((rc = run_blocks(c, engine, &xf))) return rc;
-  out_k<<<(unsigned)BN, 256, 0, c.stream>>>(WF(c.W.h), PF(L.out_w), PF(L.out_b), Fi, sizes, N, WF(c.W.hout));
-  HD_CHECK_LAUNCH();
-  vel_k<<<(unsigned)((BN * D + 255) / 256), 256, 0, c.stream>>>(xf, WF(c.W.x0), WF(c.W.hout), sizes, B, N, F,
-                                                               WF(c.W.eps_raw), nanflag);
-  HD_CHECK_LAUNCH();
-  cog_k<<<B, 128, sizeof(float) * N * D, c.stream>>>(WF(c.W.eps_raw), sizes, N, F, nanflag, eps, flags);
-  HD_CHECK_LAUNCH();
+  HD_CHECK_CUDA(launch_pdl(out_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.h), PF(L.out_w),
+                          PF(L.out_b), Fi, sizes, N, WF(c.W.hout)));
+  count_launch();
+  HD_CHECK_CUDA(launch_pdl(vel_k, dim3((unsigned)((BN * D + 255) / 256)), dim3(256), 0, c.stream, (const float*)xf,
+                          (const float*)WF(c.W.x0), (const float*)WF(c.W.hout), sizes, B, N, F, WF(c.W.eps_raw),
+                          nanflag));
+  count_launch();
+  HD_CHECK_CUDA(launch_pdl(cog_k, dim3(B), dim3(128), sizeof(float) * N * D, c.stream, (const float*)WF(c.W.eps_raw),
+                          sizes, N, F, (const int32_t*)nanflag, eps, flags));
+  count_launch();
   return HD_OK;
 }
 
@@ -539,9 +561,10 @@ HD_API int32_t hd_reverse_step(const float* zt, const float* eps, const float* r
     set_error("null argument");
     return HD_E_INVALID;
   }
-  reverse_step_k<<<B, 128, sizeof(float) * 3 * N * (3 + F), static_cast<cudaStream_t>(stream)>>>(
-      zt, eps, randn_x, randn_h, sizes, N, F, sched, sched_per_mol, zs, flags);
-  HD_CHECK_LAUNCH();
+  HD_CHECK_CUDA(launch_pdl(reverse_step_k, dim3(B), dim3(128), sizeof(float) * 3 * N * (3 + F),
+                          static_cast<cudaStream_t>(stream), zt, eps, randn_x, randn_h, sizes, N, F, sched,
+                          sched_per_mol, zs, flags));
+  count_launch();
   return HD_OK;
 }
 
@@ -567,9 +590,9 @@ HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float
     set_error("bad argument");
     return HD_E_INVALID;
   }
-  loop_fetch_k<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(counter, t_table, sched_table, B, t_cur,
-                                                                 sched_cur);
-  HD_CHECK_LAUNCH();
+  HD_CHECK_CUDA(launch_pdl(loop_fetch_k, dim3(1), dim3(128), 0, static_cast<cudaStream_t>(stream), counter, t_table,
+                          sched_table, B, t_cur, sched_cur));
+  count_launch();
   return HD_OK;
 }
 

@@ -100,6 +100,34 @@ struct Workspace {
 Workspace make_workspace(const hd_config& cfg, int B, int N);
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the per-step chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may start (barrier / TMEM set-up, weight copies)
+// while the previous kernel drains, and must call pdl_wait() before touching anything an earlier kernel wrote
+// and before their first global write.  pdl_wait() returns when the previous grid has completed and flushed;
+// completion is transitive because every kernel of the chain executes it in every CTA.  HD_NO_PDL=1 disables.
+// ---------------------------------------------------------------------------------------
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+// ---------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__

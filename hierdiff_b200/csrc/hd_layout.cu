@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include <cuda_bf16.h>
 
@@ -21,6 +22,14 @@ const char* last_error() { return g_err; }
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("HD_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 
 static int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
   const int K = p.K1 + p.K2, nch = K / KC, nch1 = p.K1 / KC;
   const int row0 = blockIdx.x * TM, ct = blockIdx.y;
   HD_STAMP(0, tid == 0);
+  pdl_trigger();   // the next kernel's CTAs may be scheduled as soon as resources free up (they wait for our completion)
 
   if (tid == 0) {
     for (int s = 0; s < NSTG; ++s) {
@@ -164,6 +165,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_relaxed(bar_full(s));
     };
+    // set-up, the weight copies (constant data) and the bias run ahead of the previous kernel's completion; the
+    // activations it produced are only read from here on, and every global write of this kernel comes later
+    pdl_wait();
     // four chunks of loads in flight per thread (the whole ring)
     float4 v0[8], v1[8], v2[8], v3[8];
     load(v0, 0);
@@ -303,8 +307,8 @@ static int launch(const Params& p, int n_out, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((p.rows + TM - 1) / TM, n_out / NT);
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(p);
-  HD_CHECK_LAUNCH();
+  HD_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), S::TOTAL, st, p));
+  count_launch();
   return HD_OK;
 }
 

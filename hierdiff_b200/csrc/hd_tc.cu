@@ -161,13 +161,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   constexpr int MMA_WARP = NPW + NEW, META_WARP = MMA_WARP + 1;
 
   // ---- one-time setup --------------------------------------------------------------------------
+  // Everything up to pdl_wait() touches only constants (weights) and on-chip state, so it overlaps the previous
+  // kernel's tail: barrier init, the resident W2 image (TMA bulk copies, 64-128 KB), the bias / weight vectors, TMEM.
+  pdl_trigger();
   for (int k = tid; k < H; k += NTHREADS) {
     s_b2[k] = p.b2[k];
     s_wa[k] = p.wa[k];
     s_wr[k] = p.wr[k];
     s_wd[k] = p.wd[k];
   }
-  for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       ptx::mbar_init(bar_full(s), NPW * CG);   // one elected arrive per producer warp of each CTA
@@ -182,7 +184,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     ptx::mbar_init(bar_tstart, NPW);
     ptx::mbar_init(bar_wr, CG);
     ptx::fence_mbar_init();
+    // resident W2 image(s): this CTA's 128-row half (CG=2) or both halves (CG=1)
+    ptx::mbar_expect_tx(bar_wl, S::W_BYTES);
+    const int nhalf = CG == 2 ? 1 : 2;
+    for (int hf = 0; hf < nhalf; ++hf) {
+      const int src_half = CG == 2 ? (int)rank : hf;
+      for (int part = 0; part < (STRICT ? 2 : 1); ++part) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(part ? p.w_lo : p.w_hi) + (size_t)src_half * W_HALF;
+        const uint32_t dst = sbase + S::OFF_W + (hf * (STRICT ? 2 : 1) + part) * W_HALF;
+        for (int off = 0; off < W_HALF; off += 16384) ptx::bulk_g2s(dst + off, src + off, 16384, bar_wl);
+      }
+    }
   }
+  pdl_wait();   // row_off, sizes, x, the A|B operands: written by earlier kernels of the chain
+  for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
   if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
@@ -560,18 +575,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      // resident W2 image(s): this CTA's 128-row half (CG=2) or both halves (CG=1)
-      const uint32_t wbytes = S::W_BYTES;
-      ptx::mbar_expect_tx(bar_wl, wbytes);
-      const int nhalf = CG == 2 ? 1 : 2;
-      for (int hf = 0; hf < nhalf; ++hf) {
-        const int src_half = CG == 2 ? (int)rank : hf;
-        for (int part = 0; part < (STRICT ? 2 : 1); ++part) {
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(part ? p.w_lo : p.w_hi) + (size_t)src_half * W_HALF;
-          const uint32_t dst = sbase + S::OFF_W + (hf * (STRICT ? 2 : 1) + part) * W_HALF;
-          for (int off = 0; off < W_HALF; off += 16384) ptx::bulk_g2s(dst + off, src + off, 16384, bar_wl);
-        }
-      }
       ptx::mbar_wait(bar_wl, 0);
       if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_wr, 0);
       else ptx::mbar_arrive(bar_wr);
@@ -638,6 +641,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 }
 
 __global__ void plan_k(const int32_t* __restrict__ sizes, int B, int32_t* __restrict__ row_off) {
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int acc = 0;
   row_off[0] = 0;
@@ -675,13 +680,15 @@ static int launch_edge(const Params& p, cudaStream_t st) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   HD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   count_launch();
   return HD_OK;
@@ -697,8 +704,9 @@ static int ensure_plan(const FwdCtx& c) {
     return HD_E_INVALID;
   }
   if (!c.planned) {
-    tc::plan_k<<<1, 32, 0, c.stream>>>(c.sizes, c.B, reinterpret_cast<int32_t*>(c.ws + c.W.row_off));
-    HD_CHECK_LAUNCH();
+    HD_CHECK_CUDA(launch_pdl(tc::plan_k, dim3(1), dim3(32), 0, c.stream, c.sizes, c.B,
+                            reinterpret_cast<int32_t*>(c.ws + c.W.row_off)));
+    count_launch();
     c.planned = true;
   }
   return HD_OK;
