@@ -189,3 +189,62 @@ def test_flags_report_violations(tmp_path):
     eps = model.phi(z, s, nm, em, None)
     assert model.dynamics.nan_guard_fired()
     assert torch.all(eps[..., :3] == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: node-count sweep at batch 128, plus the limits of the tensor-core engines
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [16, 24, 32, 40, 56])
+def test_node_count_sweep_tracks_fp32_engine(model4, N):
+    """B=128, N in {16,24,32,40,56}: strict tensor-core engine vs the fp32 FFMA engine; ragged sizes, zero padding."""
+    B = 128
+    rng = np.random.default_rng(N)
+    sizes = rng.integers(1, N + 1, B).astype(np.int32)
+    sizes[:8] = N
+    z, t = random_batch(B, N, sizes, seed=300 + N)
+    use(model4, "fp32")
+    ref = fwd(model4, z, t, sizes)
+    use(model4, "strict")
+    got = fwd(model4, z, t, sizes)
+    assert rel(got, ref) < 5e-5
+    for b in range(B):
+        assert np.all(got[b, sizes[b]:] == 0)
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 128), (255, 3), (7, 100)])
+def test_extreme_shapes(model4, B, N):
+    """Smallest / largest supported shapes (N <= 128, B <= 255 per call on the tensor-core engines)."""
+    rng = np.random.default_rng(B * 1000 + N)
+    sizes = rng.integers(1, N + 1, B).astype(np.int32)
+    sizes[0] = N
+    z, t = random_batch(B, N, sizes, seed=B + N)
+    use(model4, "fp32")
+    ref = fwd(model4, z, t, sizes)
+    use(model4, "strict")
+    got = fwd(model4, z, t, sizes)
+    assert np.isfinite(got).all()
+    assert rel(got, ref) < 5e-5
+
+
+def test_too_many_molecules_is_an_error_not_a_fallback(model4):
+    from hierdiff_b200 import native
+    B, N = 256, 2
+    sizes = np.full(B, N, np.int32)
+    z, t = random_batch(B, N, sizes, seed=5)
+    use(model4, "strict")
+    with pytest.raises(native.NativeError, match="at most 255"):
+        fwd(model4, z, t, sizes)
+
+
+@pytest.mark.parametrize("engine", ["strict", "fast"])
+def test_forward_is_bitwise_reproducible(model4, engine):
+    """The j-reduction never crosses a CTA and uses no atomics: 20 repetitions are bit-identical (also a stress test
+    of the mbarrier hand-offs between producer / MMA / epilogue warps)."""
+    B, N = 64, 40
+    rng = np.random.default_rng(11)
+    sizes = rng.integers(1, N + 1, B).astype(np.int32)
+    z, t = random_batch(B, N, sizes, seed=12)
+    use(model4, engine)
+    first = fwd(model4, z, t, sizes)
+    for _ in range(20):
+        assert np.array_equal(fwd(model4, z, t, sizes), first)
