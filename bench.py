@@ -93,6 +93,51 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_torch_eager(args):
+    """GPU comparator of BASELINE.md 4 (">= 10x the reference single-GPU PyTorch"): oracle/torch_port.py issues the
+    reference's per-step ATen operator sequence (dense edge index, gathers, cat, Linear, scatter_add_, host syncs)
+    in eager PyTorch on cuda:0.  A bounded number of reverse steps is timed and extrapolated to T=1000."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from oracle import torch_port
+    dev = torch.device("cuda", 0)
+    B, N = B_PER_GPU, N_NODES
+    port = torch_port.build(N_LAYERS, dev)
+    nm, em = torch_port.masks([N] * B, N, dev)
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.manual_seed(0)
+        z = torch.randn(B, N, 11, device=dev)
+        z[..., :3] -= z[..., :3].mean(1, keepdim=True)
+        t = torch.full((B, 1), 0.5, device=dev)
+        sched = (1.0005, 0.01, 0.02)
+        n_steps = 10
+        with torch.no_grad():
+            for _ in range(3):
+                port.reverse_step(z, t, sched, nm, em)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n_steps):
+                z2 = port.reverse_step(z, t, sched, nm, em)
+            b.record()
+            torch.cuda.synchronize()
+        ms_step = a.elapsed_time(b) / n_steps
+        out["tf32" if tf32 else "fp32"] = {"ms_per_reverse_step": ms_step,
+                                           "molecules_per_s": B / (ms_step * 1e-3 * (T_STEPS + 1))}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    line = {"impl": "torch-eager", "metric": METRIC, "value": out["fp32"]["molecules_per_s"], "unit": UNIT,
+            "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1), "detail": out,
+            "note": "operator-for-operator PyTorch restatement of the reference step (oracle/torch_port.py, pinned "
+                    "against the golden fixtures), eager on cuda:0, 10 reverse steps timed with CUDA events and "
+                    "extrapolated x1001; 'tf32' = torch.backends.cuda.matmul.allow_tf32 (the reference's torch-1.9 "
+                    "default on Ampere)"}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
@@ -312,7 +357,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--engine", default=os.environ.get("HD_BENCH_ENGINE", "strict"), choices=["strict", "fast", "fp32"])
     ap.add_argument("--steps-per-graph", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -323,6 +368,8 @@ def main():
     T_STEPS = args.timesteps
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-eager":
+        run_torch_eager(args)
     else:
         run_ours(args)
 

@@ -122,3 +122,19 @@ def test_schedule_scalars_match_torch():
         want = np.array([al.item(), (s2 / al / st).item(), (torch.sqrt(s2) * ss / st).item()], np.float32)
         got = O.step_scalars(gs, gt)[0]
         assert np.allclose(got, want, rtol=2e-6, atol=1e-7), (gs, gt, got, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# the plain-PyTorch restatement (oracle/torch_port.py, the GPU comparator of bench.py --impl torch-eager)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["forward_l2", "forward_l1_pad"])
+def test_torch_port_matches_reference(golden_dir, name):
+    import torch
+    from oracle import torch_port
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    port = torch_port.build(int(g["n_layers"]), "cpu")
+    z, t, sizes = torch.from_numpy(g["z"]), torch.from_numpy(g["t"]), g["sizes"]
+    nm, em = torch_port.masks(sizes, z.shape[1], "cpu")
+    eps = port.dynamics(t.view(-1, 1), z, nm, em)
+    err = np.abs(eps.numpy() - g["eps"]).max() / np.abs(g["eps"]).max()
+    assert err < 2e-6, err
