@@ -214,6 +214,14 @@ def run_ours(args):
 
     B, N = B_PER_GPU, N_NODES
     sizes_pinned = torch.full((B,), N, dtype=torch.int32).pin_memory()
+    if args.sizes == "geom":     # secondary workload of SURVEY.md 8d: GEOM size histogram clipped to N, max forced to N
+        import numpy as np
+        g = np.load(os.path.join(ROOT, "tests", "golden", "nodes_dist.npz"))
+        keys, cnt = g["hist_keys"].astype(np.int64), g["hist_counts"].astype(np.float64)
+        draw = np.random.default_rng(ctx.rank).choice(keys, size=B, p=cnt / cnt.sum())
+        draw = np.minimum(draw, N)
+        draw[0] = N
+        sizes_pinned = torch.from_numpy(draw.astype(np.int32)).pin_memory()
     loop = model.sampling_loop(B, N, dev)        # builds the schedule table, captures the graph (untimed)
     L = native.lib()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -279,7 +287,8 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": {"strict": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate)",
                           "fast": "bf16 operands, fp32 accumulate", "fp32": "f32"}[engine],
-                "data": "synthetic", "config": workload_config(ctx.world, engine),
+                "data": "synthetic", "config": dict(workload_config(ctx.world, engine), sizes=args.sizes,
+                                                    mean_nodes=float(sizes_pinned.float().mean())),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(sizes_pinned.numel() * 4),
                         "d2h_bytes_per_step": int(B * N * 11 * 4 + 4), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int((per_step * T_STEPS + per_final + 1) * args.steps * 2),
@@ -318,9 +327,11 @@ def edge_kernel_roofline(model, loop, engine, B, N, iters=20):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / iters
-    edges = B * N * N
+    n = loop.sizes.double()
+    edges = float((n * n).sum())                              # real (i,j) pairs, i == j included (en_dynamics.py:131-136)
+    nodes = float(n.sum())
     flops = 2.0 * edges * HIDDEN * HIDDEN                     # dense [E,256]x[256,256] contraction
-    hbm_bytes = B * N * (2 * HIDDEN * 4 + HIDDEN * 4 + 24) + 4 * HIDDEN * HIDDEN   # A|B in, agg out, x/x0, W2
+    hbm_bytes = nodes * (2 * HIDDEN * 4 + HIDDEN * 4 + 24) + 4 * HIDDEN * HIDDEN   # A|B in, agg out, x/x0, W2
     peaks, src = {}, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -362,6 +373,8 @@ def main():
     ap.add_argument("--steps-per-graph", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the loop eagerly (profiling under ncu)")
+    ap.add_argument("--sizes", default="full", choices=["full", "geom"],
+                    help="full: every molecule has N nodes (headline); geom: sizes from the GEOM histogram, padded to N")
     ap.add_argument("--timesteps", type=int, default=T_STEPS,
                     help="profiling only: a shorter chain (the JSON line then names the shortened workload)")
     args = ap.parse_args()
