@@ -39,11 +39,15 @@ __device__ long long g_acc[2][3][16];   // [CTA 10 | CTA 11][role][slot]
 #endif
 
 constexpr int TILE_M = 128;           // edge rows per CTA tile
-constexpr int KCH = 32;               // K columns per operand stage
-constexpr int NCH = H / KCH;          // 8 stages per tile
-constexpr int NSTAGE = 4;             // operand ring depth
+#ifndef HD_KCH
+#define HD_KCH 64
+#endif
+constexpr int KCH = HD_KCH;           // K columns per operand stage (one producer -> MMA hand-off)
+constexpr int NCH = H / KCH;          // stages per tile
+constexpr int NSTAGE = 128 / KCH;     // operand ring depth: 128 K-columns in flight
+constexpr int HSPS = KCH / 16;        // 16-column half steps per stage
 constexpr int A_KG = 2048;            // bytes between K-adjacent core matrices of A (128 rows x 16 B)
-constexpr int A_HALF = 4 * A_KG;      // one stage of hi (or lo): 4 core-matrix columns = 8 KB
+constexpr int A_HALF = (KCH / 8) * A_KG;   // one stage of hi (or lo): KCH/8 core-matrix columns
 constexpr int W_KG = 2048;            // bytes between K-adjacent core matrices of a 128-row W half image
 constexpr int W_HALF = (H / 8) * W_KG;  // 64 KB: one 128-row half image (hi or lo)
 constexpr int PMETA_BUFS = 2;         // producer-side row metadata: tiles t, t+1
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
     // MUFU latencies of the chains overlap
     auto half_step = [&](const float4 (&v)[4], const RowState& r, int hs, int s) {
-      const int ph = hs & 1;
+      const int ph = hs % HSPS;
       const int k0 = 16 * hs + 4 * qsub;
       const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
       const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
@@ -352,24 +356,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int gc = t * NCH + c, st = gc % NSTAGE;
-        load_half(vb, cur, 2 * c + 1);
-        HD_ACC(0, 5, tid == 0);   // issue loads
-        ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
-        HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
-        half_step(va, cur, 2 * c, st);
-        HD_ACC(0, 2, tid == 0);   // half steps
-        if (pending >= 0) publish(pending);
-        HD_ACC(0, 3, tid == 0);   // publish
-        if (c + 1 < NCH) {
-          load_half(va, cur, 2 * c + 2);
-        } else if (t + 1 < ntiles) {   // first operands of the next tile, so the tile boundary costs no load latency
-          ptx::mbar_wait(bar_meta, (t + 1) & 1);
-          read_meta(t + 1, nxt);
-          load_half(va, nxt, 0);
+#pragma unroll
+        for (int pp = 0; pp < HSPS / 2; ++pp) {
+          const int hs0 = c * HSPS + 2 * pp;
+          load_half(vb, cur, hs0 + 1);
+          HD_ACC(0, 5, tid == 0);   // issue loads
+          if (pp == 0) ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
+          HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
+          half_step(va, cur, hs0, st);
+          HD_ACC(0, 2, tid == 0);   // half steps
+          if (pp == 0 && pending >= 0) publish(pending);
+          HD_ACC(0, 3, tid == 0);   // publish
+          if (pp + 1 < HSPS / 2 || c + 1 < NCH) {
+            load_half(va, cur, hs0 + 2);
+          } else if (t + 1 < ntiles) {   // first operands of the next tile: the tile boundary costs no load latency
+            ptx::mbar_wait(bar_meta, (t + 1) & 1);
+            read_meta(t + 1, nxt);
+            load_half(va, nxt, 0);
+          }
+          HD_ACC(0, 5, tid == 0);
+          half_step(vb, cur, hs0 + 1, st);
+          HD_ACC(0, 2, tid == 0);
         }
-        HD_ACC(0, 5, tid == 0);
-        half_step(vb, cur, 2 * c + 1, st);
-        HD_ACC(0, 2, tid == 0);
         pending = st;
       }
       if (t + 1 < ntiles) {
@@ -594,9 +602,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
             HD_ACC(2, 1, true);   // wait for operands
             const uint32_t a_hi = sbase + S::OFF_A + s * S::STAGE;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
+            for (int ks = 0; ks < KCH / 16; ++ks) {
               const uint32_t acc_on = (c | ks) ? 1u : 0u;
-              const uint32_t kgw = (c * 4 + ks * 2) * W_KG;
+              const uint32_t kgw = (c * (KCH / 8) + ks * 2) * W_KG;
               const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 2 * A_KG, A_KG, 128);
               const uint64_t da_lo = ptx::smem_desc(a_hi + A_HALF + ks * 2 * A_KG, A_KG, 128);
               if constexpr (CG == 2) {
