@@ -8,6 +8,7 @@
 namespace hd {
 void set_error(const char*, ...) {}
 void count_launch() {}
+bool pdl_enabled() { return false; }
 int linear_tc(const FwdCtx&, const float*, int, int, const float*, int, int, const void*, const void*, int, int,
               const float*, float*, int, int, const float*, bool) { return 0; }
 }
@@ -22,7 +23,13 @@ static void run(const char* name, hd::tc::Params p) {
   for (int it = 0; it < 3; ++it) {
     cudaMemcpyToSymbol(tc::g_acc, zero, sizeof(zero));
     cudaEventRecord(e0);
-    for (int k = 0; k < 10; ++k) tc::launch_edge<GCL, STRICT, 2>(p, 0);
+    for (int k = 0; k < 10; ++k) {
+#ifdef HD_UNIFORM
+      tc::launch_edge_u<GCL, STRICT, 2>(p, 0);
+#else
+      tc::launch_edge<GCL, STRICT, 2>(p, 0);
+#endif
+    }
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     cudaEventElapsedTime(&ms, e0, e1);
@@ -33,7 +40,11 @@ static void run(const char* name, hd::tc::Params p) {
   long long (*acc)[16] = acc2[cta];
   printf(" -- CTA %d (cluster rank %d)\n", 10 + cta, cta);
   printf("%s: %.2f us/launch; err=%s  (cycles per launch)\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
+  #ifdef HD_UNIFORM
+  const char* pn[] = {"wait accumulator", "wait empty stage", "build steps", "publish", "epilogue parts", "issue loads"};
+#else
   const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier", "issue loads"};
+#endif
   const char* en[] = {"wait accumulator", "pass 1", "dot exchange", "pass 2", "scratch barrier", "combine+release"};
   const char* mn[] = {"wait free acc", "wait operands", "issue"};
   long long s = 0;

@@ -52,4 +52,5 @@ int main() {
 namespace hd {  // stubs for symbols hd_node.cu references
 void set_error(const char*, ...) {}
 void count_launch() {}
+bool pdl_enabled() { return false; }
 }
