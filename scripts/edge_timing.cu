@@ -23,13 +23,7 @@ static void run(const char* name, hd::tc::Params p) {
   for (int it = 0; it < 3; ++it) {
     cudaMemcpyToSymbol(tc::g_acc, zero, sizeof(zero));
     cudaEventRecord(e0);
-    for (int k = 0; k < 10; ++k) {
-#ifdef HD_UNIFORM
-      tc::launch_edge_u<GCL, STRICT, 2>(p, 0);
-#else
-      tc::launch_edge<GCL, STRICT, 2>(p, 0);
-#endif
-    }
+    for (int k = 0; k < 10; ++k) tc::launch_edge<GCL, STRICT, 2>(p, 0);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     cudaEventElapsedTime(&ms, e0, e1);
@@ -40,11 +34,7 @@ static void run(const char* name, hd::tc::Params p) {
   long long (*acc)[16] = acc2[cta];
   printf(" -- CTA %d (cluster rank %d)\n", 10 + cta, cta);
   printf("%s: %.2f us/launch; err=%s  (cycles per launch)\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
-  #ifdef HD_UNIFORM
-  const char* pn[] = {"wait accumulator", "wait empty stage", "build steps", "publish", "epilogue parts", "issue loads"};
-#else
-  const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier", "issue loads"};
-#endif
+    const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier", "issue loads"};
   const char* en[] = {"wait accumulator", "pass 1", "dot exchange", "pass 2", "scratch barrier", "combine+release"};
   const char* mn[] = {"wait free acc", "wait operands", "issue"};
   long long s = 0;
