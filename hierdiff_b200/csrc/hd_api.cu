@@ -16,7 +16,7 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
 // ---------------------------------------------------------------------------------------
 __global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t, const int32_t* __restrict__ sizes,
                        int B, int N, int F, float* __restrict__ hin, float* __restrict__ x, float* __restrict__ x0,
-                       int32_t* __restrict__ nanflag) {
+                       float* __restrict__ x2, int32_t* __restrict__ nanflag) {
   pdl_wait();
   pdl_trigger();
   const int D = 3 + F, Fi = F + 1;
@@ -31,6 +31,7 @@ __global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t,
     const float v = z[r * D + ch] * mk;
     x[r * 3 + ch] = v;
     x0[r * 3 + ch] = v;
+    x2[r * 3 + ch] = 0.f;   // ping-pong buffer of the coordinate updates: padded rows stay 0
   } else if (ch < D) {
     hin[r * Fi + (ch - 3)] = z[r * D + ch] * mk;
   } else {
@@ -406,13 +407,14 @@ HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, con
   if (!make_layout(*cfg, &L)) return HD_E_INVALID;
   FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
            sizes, B, N, static_cast<cudaStream_t>(stream)};
+  c.x_prezeroed = true;   // prep_k below writes x (masked) and zeroes x2
   const int Fi = cfg->in_node_nf, F = Fi - 1, D = 3 + F;
   const int64_t BN = (int64_t)B * N;
   auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
   auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   int32_t* nanflag = reinterpret_cast<int32_t*>(c.ws + c.W.nanflag);
   HD_CHECK_CUDA(launch_pdl(prep_k, dim3((unsigned)((BN * (D + 1) + 255) / 256)), dim3(256), 0, c.stream, z, t, sizes, B, N,
-                          F, WF(c.W.hin), WF(c.W.x), WF(c.W.x0), nanflag));
+                          F, WF(c.W.hin), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), nanflag));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.hin), Fi,
                           PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h)));

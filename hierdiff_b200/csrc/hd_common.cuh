@@ -153,6 +153,8 @@ struct FwdCtx {
   int B, N;
   cudaStream_t stream;
   mutable bool planned = false;  // ws.row_off holds the edge-row prefix for `sizes`
+  bool x_prezeroed = false;      // padded rows of ws.x / ws.x2 are already 0 (hd_dynamics_forward): the coordinate
+                                 // update then needs no memset of its output
 };
 
 // GCL sub-layer `si` (index into L.subs) in place on ctx.ws h; reads x (ws.x) and x0.

@@ -752,7 +752,8 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   if (S.is_gcl) {
     return strict ? tc::launch_edge<true, true, 2>(p, c.stream) : tc::launch_edge<true, false, 2>(p, c.stream);
   }
-  HD_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 3 * c.B * c.N, c.stream));  // padded rows: x*mask = 0
+  if (!c.x_prezeroed)   // padded rows: x*mask = 0 (the kernel only writes the rows of real receivers)
+    HD_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 3 * c.B * c.N, c.stream));
   return strict ? tc::launch_edge<false, true, 2>(p, c.stream) : tc::launch_edge<false, false, 2>(p, c.stream);
 }
 
