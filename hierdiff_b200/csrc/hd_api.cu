@@ -14,17 +14,18 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
 // ---------------------------------------------------------------------------------------
 // en_dynamics.py:56-74: xh*node_mask, split, append time.  One thread per (row, channel).
 // ---------------------------------------------------------------------------------------
-__global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t, const int32_t* __restrict__ sizes,
-                       int B, int N, int F, float* __restrict__ hin, float* __restrict__ x, float* __restrict__ x0,
-                       float* __restrict__ x2, int32_t* __restrict__ nanflag) {
+__global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t, const float* __restrict__ context,
+                       int C, const int32_t* __restrict__ sizes, int B, int N, int F, float* __restrict__ hin,
+                       float* __restrict__ x, float* __restrict__ x0, float* __restrict__ x2,
+                       int32_t* __restrict__ nanflag) {
   pdl_wait();
   pdl_trigger();
-  const int D = 3 + F, Fi = F + 1;
+  const int D = 3 + F, Fi = F + 1 + C, W = D + 1 + C;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) *nanflag = 0;
-  if (idx >= (int64_t)B * N * (D + 1)) return;
-  const int64_t r = idx / (D + 1);
-  const int ch = (int)(idx % (D + 1));
+  if (idx >= (int64_t)B * N * W) return;
+  const int64_t r = idx / W;
+  const int ch = (int)(idx % W);
   const int b = (int)(r / N), i = (int)(r % N);
   const float mk = i < sizes[b] ? 1.f : 0.f;
   if (ch < 3) {
@@ -34,8 +35,10 @@ __global__ void prep_k(const float* __restrict__ z, const float* __restrict__ t,
     x2[r * 3 + ch] = 0.f;   // ping-pong buffer of the coordinate updates: padded rows stay 0
   } else if (ch < D) {
     hin[r * Fi + (ch - 3)] = z[r * D + ch] * mk;
-  } else {
+  } else if (ch == D) {
     hin[r * Fi + F] = t[b];  // time channel is not masked (en_dynamics.py:66-74)
+  } else {
+    hin[r * Fi + F + (ch - D)] = context[r * C + (ch - D - 1)];  // nor is the context (en_dynamics.py:76-79)
   }
 }
 
@@ -76,11 +79,11 @@ __global__ void __launch_bounds__(256) out_k(const float* __restrict__ h, const 
 
 // en_dynamics.py:89,103-111: vel = (x_final - x)*mask, drop the time channel, NaN detection.
 __global__ void vel_k(const float* __restrict__ xf, const float* __restrict__ x0, const float* __restrict__ hout,
-                      const int32_t* __restrict__ sizes, int B, int N, int F, float* __restrict__ eps_raw,
+                      const int32_t* __restrict__ sizes, int B, int N, int F, int Fi, float* __restrict__ eps_raw,
                       int32_t* __restrict__ nanflag) {
   pdl_wait();
   pdl_trigger();
-  const int D = 3 + F, Fi = F + 1;
+  const int D = 3 + F;   // the first F of the Fi output channels: time and context are sliced off (en_dynamics.py:99-105)
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * N * D) return;
   const int64_t r = idx / D;
@@ -397,10 +400,21 @@ HD_API int64_t hd_workspace_bytes(const hd_config* cfg, int32_t B, int32_t N) {
 HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, const float* z, const float* t,
                             const int32_t* sizes, int32_t B, int32_t N, float* eps, void* workspace,
                             int32_t* flags, int32_t engine, hd_stream_t stream) {
+  return hd_dynamics_forward_ctx(cfg, packed, z, t, nullptr, 0, sizes, B, N, eps, workspace, flags, engine, stream);
+}
+
+HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed, const float* z, const float* t,
+                                const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
+                                int32_t N, float* eps, void* workspace, int32_t* flags, int32_t engine,
+                                hd_stream_t stream) {
   int rc = check_common(cfg, packed, sizes, B, N, engine);
   if (rc) return rc;
   if (!z || !t || !eps || !workspace) {
     set_error("null argument");
+    return HD_E_INVALID;
+  }
+  if (context_nf < 0 || (context_nf > 0 && !context) || cfg->in_node_nf - 1 - context_nf < 0) {
+    set_error("bad context (context_nf=%d, in_node_nf=%d)", context_nf, cfg->in_node_nf);
     return HD_E_INVALID;
   }
   Layout L;
@@ -408,13 +422,13 @@ HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, con
   FwdCtx c{cfg, &L, static_cast<const char*>(packed), static_cast<char*>(workspace), make_workspace(*cfg, B, N),
            sizes, B, N, static_cast<cudaStream_t>(stream)};
   c.x_prezeroed = true;   // prep_k below writes x (masked) and zeroes x2
-  const int Fi = cfg->in_node_nf, F = Fi - 1, D = 3 + F;
+  const int Fi = cfg->in_node_nf, C = context_nf, F = Fi - 1 - C, D = 3 + F;
   const int64_t BN = (int64_t)B * N;
   auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
   auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   int32_t* nanflag = reinterpret_cast<int32_t*>(c.ws + c.W.nanflag);
-  HD_CHECK_CUDA(launch_pdl(prep_k, dim3((unsigned)((BN * (D + 1) + 255) / 256)), dim3(256), 0, c.stream, z, t, sizes, B, N,
-                          F, WF(c.W.hin), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), nanflag));
+  HD_CHECK_CUDA(launch_pdl(prep_k, dim3((unsigned)((BN * (D + 1 + C) + 255) / 256)), dim3(256), 0, c.stream, z, t, context,
+                          C, sizes, B, N, F, WF(c.W.hin), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), nanflag));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.hin), Fi,
                           PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h)));
@@ -425,7 +439,7 @@ HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, con
                           PF(L.out_b), Fi, sizes, N, WF(c.W.hout)));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(vel_k, dim3((unsigned)((BN * D + 255) / 256)), dim3(256), 0, c.stream, (const float*)xf,
-                          (const float*)WF(c.W.x0), (const float*)WF(c.W.hout), sizes, B, N, F, WF(c.W.eps_raw),
+                          (const float*)WF(c.W.x0), (const float*)WF(c.W.hout), sizes, B, N, F, Fi, WF(c.W.eps_raw),
                           nanflag));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(cog_k, dim3(B), dim3(128), sizeof(float) * N * D, c.stream, (const float*)WF(c.W.eps_raw),

@@ -184,8 +184,8 @@ class DiffusionQM9(nn.Module):
     @torch.no_grad()
     def sample_p_zs_given_zt(self, s, t, zt, node_mask, edge_mask, context, fix_noise=False, mol_shape=None):
         """diffusion_qm9.py:312-345: one ancestral step, eager (per-molecule schedule rows like the reference)."""
-        if context is not None or fix_noise:
-            raise NotImplementedError("context / fix_noise are not built")
+        if fix_noise:
+            raise NotImplementedError("fix_noise is not built")
         B, N, _ = zt.shape
         if mol_shape is not None and mol_shape != N:
             raise NotImplementedError("pocket conditioning (mol_shape < n_nodes) is not built yet")
@@ -196,7 +196,7 @@ class DiffusionQM9(nn.Module):
         sched = torch.empty(B, 3, device=zt.device)
         flags = torch.zeros(1, dtype=torch.int32, device=zt.device)
         zt = zt.contiguous().float()
-        eps = self.dynamics.forward_sizes(t, zt, sizes, flags=flags)
+        eps = self.dynamics.forward_sizes(t, zt, sizes, flags=flags, context=context)
         rx, rh = self._draw(B, N, zt.device)
         zs = torch.empty_like(zt)
         with torch.cuda.device(zt.device):
@@ -212,8 +212,8 @@ class DiffusionQM9(nn.Module):
     @torch.no_grad()
     def sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise=False):
         """diffusion_qm9.py:294-310."""
-        if context is not None or fix_noise:
-            raise NotImplementedError("context / fix_noise are not built")
+        if fix_noise:
+            raise NotImplementedError("fix_noise is not built")
         B, N, _ = z0.shape
         L = native.lib()
         sizes = self._masks_to_sizes(node_mask, edge_mask)
@@ -222,7 +222,7 @@ class DiffusionQM9(nn.Module):
         sched = torch.empty(B, 3, device=z0.device)
         flags = torch.zeros(1, dtype=torch.int32, device=z0.device)
         z0 = z0.contiguous().float()
-        eps = self.dynamics.forward_sizes(zeros, z0, sizes, flags=flags)
+        eps = self.dynamics.forward_sizes(zeros, z0, sizes, flags=flags, context=context)
         rx, rh = self._draw(B, N, z0.device)
         x = torch.empty(B, N, self.n_dims, device=z0.device)
         h = torch.empty(B, N, self.in_node_nf, device=z0.device)
@@ -254,14 +254,15 @@ class DiffusionQM9(nn.Module):
         return loop
 
     @torch.no_grad()
-    def sample_padded(self, sample_n, device, z_T=None):
-        """The chain for given molecule sizes; returns padded CPU tensors x [B,N,3], h [B,N,F]."""
+    def sample_padded(self, sample_n, device, z_T=None, context=None):
+        """The chain for given molecule sizes; returns padded CPU tensors x [B,N,3], h [B,N,F].
+        ``context``: None, or anything broadcastable to [B,N,context_node_nf] (diffusion_qm9.py:351-352)."""
         device = torch.device(device)
         if device.type != "cuda":
             raise native.NativeError("sampling runs on a CUDA device only (no CPU fallback)")
         B, N = len(sample_n), max(sample_n)
         loop = self.sampling_loop(B, N, device)
-        x, h, flags = loop.run(sample_n, z_T=z_T)
+        x, h, flags = loop.run(sample_n, z_T=z_T, context=context)
         out = torch.cat([x.reshape(B * N, -1), h.reshape(B * N, -1)], dim=1).cpu()   # one D2H (syncs)
         self._raise_on_flags(flags)
         return out[:, :self.n_dims].reshape(B, N, -1), out[:, self.n_dims:].reshape(B, N, -1)
@@ -269,17 +270,24 @@ class DiffusionQM9(nn.Module):
     @torch.no_grad()
     def sample(self, num_samples, device, context=None, pocket_cond=None):
         """diffusion_qm9.py:347-395: list of {'x': [n_i,3], 'h': [n_i,F]} CPU tensors."""
-        if context is not None or pocket_cond is not None:
-            raise NotImplementedError("context / pocket conditioning are not built yet")
+        if pocket_cond is not None:
+            raise NotImplementedError("pocket conditioning is not built yet")
         sample_n = self.nodes_dist.sample(num_samples)
-        x, h = self.sample_padded(sample_n, device)
-        return [{"x": x[i, :n].clone(), "h": h[i, :n].clone()} for i, n in enumerate(sample_n)]
+        if context is not None:   # "only for global context" (:351-352): broadcast over molecules and nodes
+            context = torch.zeros(num_samples, max(sample_n), 1) + torch.as_tensor(context, dtype=torch.float32).cpu()
+        x, h = self.sample_padded(sample_n, device, context=context)
+        res = [{"x": x[i, :n].clone(), "h": h[i, :n].clone()} for i, n in enumerate(sample_n)]
+        if context is not None:
+            for i, n in enumerate(sample_n):
+                res[i]["context"] = context[i, :n].clone()
+        return res
 
     def sample_batches(self, batch_size, num_batches, device, context_range=None, protein_data_all=None):
         """diffusion_qm9.py:397-436: ``(results, test_names)``."""
-        if protein_data_all is not None or context_range is not None:
-            raise NotImplementedError("protein / context conditioned sampling is not built yet")
+        if protein_data_all is not None:
+            raise NotImplementedError("protein (pocket) conditioned sampling is not built yet")
         results, test_names = [], []
-        for _ in range(num_batches):
-            results.extend(self.sample(batch_size, device))
+        for i in range(num_batches):
+            ctx = None if context_range is None else context_range[i % len(context_range)]
+            results.extend(self.sample(batch_size, device, context=ctx))
         return results, test_names

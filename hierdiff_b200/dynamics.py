@@ -24,8 +24,6 @@ class EGNN_dynamics_QM9(nn.Module):
             raise NotImplementedError(f"mode={mode!r}: only 'egnn_dynamics' (the shipped config) is built")
         if n_dims != 3:
             raise NotImplementedError("n_dims must be 3")
-        if context_node_nf:
-            raise NotImplementedError("context conditioning (context_node_nf > 0) is not built yet")
         if not condition_time:
             raise NotImplementedError("condition_time=False is not built")
         self.mode = mode
@@ -51,11 +49,17 @@ class EGNN_dynamics_QM9(nn.Module):
     def unwrap_forward(self):
         return self._forward
 
-    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None):
-        """``_forward`` with the masks already reduced to ``sizes`` [B] int32 (no validation, no sync)."""
+    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None, context=None):
+        """``_forward`` with the masks already reduced to ``sizes`` [B] int32 (no validation, no sync).
+        ``context`` [B,N,context_node_nf] is appended, unmasked, after the time channel (en_dynamics.py:76-79)."""
         native.require_cuda(xh)
         B, N, D = xh.shape
         assert D == self.n_dims + self.in_node_nf - 1, (D, self.in_node_nf)
+        C = self.context_node_nf
+        if (context is None) != (C == 0):
+            raise ValueError(f"context_node_nf={C} but context is {'missing' if context is None else 'given'}")
+        if context is not None:
+            context = context.to(xh.device, torch.float32).expand(B, N, C).contiguous()
         xh = xh.contiguous().float()
         t = t.reshape(-1).float()
         if t.numel() == 1:
@@ -64,23 +68,22 @@ class EGNN_dynamics_QM9(nn.Module):
         eps = torch.empty_like(xh) if out is None else out
         egnn = self.egnn
         with torch.cuda.device(xh.device):
-            native.check(native.lib().hd_dynamics_forward(
+            native.check(native.lib().hd_dynamics_forward_ctx(
                 egnn.hd_config(), native.ptr(egnn.packed_weights()), native.ptr(xh), native.ptr(t),
-                native.ptr(sizes), B, N, native.ptr(eps), native.ptr(egnn.workspace(B, N, xh.device)),
-                native.ptr(flags), egnn.engine_id(engine), native.stream_ptr()), "hd_dynamics_forward")
+                native.ptr(context), C, native.ptr(sizes), B, N, native.ptr(eps),
+                native.ptr(egnn.workspace(B, N, xh.device)), native.ptr(flags), egnn.engine_id(engine),
+                native.stream_ptr()), "hd_dynamics_forward_ctx")
         return eps
 
     def _forward(self, t, xh, node_mask, edge_mask, context, mol_shape=None):
         """en_dynamics.py:49-122."""
-        if context is not None:
-            raise NotImplementedError("context conditioning is not built yet")
         B, N, _ = xh.shape
         if mol_shape is not None and mol_shape != N:
             raise NotImplementedError("pocket conditioning (mol_shape < n_nodes) is not built yet")
         sizes = sizes_from_node_mask(node_mask, B, N)
         check_edge_mask(edge_mask, sizes, B, N)
         flags = torch.zeros(1, dtype=torch.int32, device=xh.device)
-        eps = self.forward_sizes(t, xh, sizes, flags=flags)
+        eps = self.forward_sizes(t, xh, sizes, flags=flags, context=context)
         self.last_flags = flags  # checked lazily: reading it here would force a host sync per call
         return eps
 

@@ -61,6 +61,8 @@ class SamplingLoop:
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
         self.flags = torch.zeros(1, dtype=torch.int32, device=device)
         self.sizes = torch.full((B,), N, dtype=torch.int32, device=device)
+        C = model.dynamics.context_node_nf
+        self.context = torch.zeros(B, N, C, **f32) if C else None   # static buffer read by the captured graph
         self.x_out = torch.zeros(B, N, 3, **f32)
         self.h_out = torch.zeros(B, N, self.F, **f32)
         self.table = None
@@ -76,7 +78,7 @@ class SamplingLoop:
         st = native.stream_ptr()
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
                                      self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
-        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps)
+        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context)
         self.rx.normal_()
         self.rh.normal_()
         native.check(L.hd_reverse_step(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
@@ -89,7 +91,7 @@ class SamplingLoop:
         st = native.stream_ptr()
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
                                      self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
-        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps)
+        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context)
         self.rx.normal_()
         self.rh.normal_()
         nv, nb = m.norm_values, m.norm_biases
@@ -129,11 +131,16 @@ class SamplingLoop:
             with torch.cuda.device(self.device):
                 self._capture(k)
 
-    def run(self, sizes_host, z_T=None):
+    def run(self, sizes_host, z_T=None, context=None):
         """Run the whole chain; returns padded (x [B,N,3], h [B,N,F]) on the device and the status word."""
         T = self.table.T
+        if (context is None) != (self.context is None):
+            raise ValueError("context must be given exactly when the dynamics has context_node_nf > 0")
         with torch.cuda.device(self.device):
             self.sizes.copy_(torch.as_tensor(sizes_host, dtype=torch.int32), non_blocking=True)
+            if context is not None:
+                self.context.copy_(torch.as_tensor(context, dtype=torch.float32).expand_as(self.context),
+                                   non_blocking=True)
             self.counter.zero_()
             self.flags.zero_()
             if z_T is None:

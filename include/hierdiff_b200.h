@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 1
+#define HD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -100,6 +100,14 @@ HD_API int64_t hd_workspace_bytes(const hd_config* cfg, int32_t B, int32_t N);
 HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, const float* z, const float* t,
                             const int32_t* sizes, int32_t B, int32_t N, float* eps, void* workspace,
                             int32_t* flags, int32_t engine, hd_stream_t stream);
+
+/* The same with conditioning (en_dynamics.py:76-79, :99-101): `context` [B,N,context_nf] is appended, unmasked, after
+ * the time channel, so in_node_nf = F + 1 + context_nf; the context channels are sliced off the output again.
+ * z / eps stay [B,N,3+F].  context may be NULL when context_nf == 0. */
+HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed, const float* z, const float* t,
+                                const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
+                                int32_t N, float* eps, void* workspace, int32_t* flags, int32_t engine,
+                                hd_stream_t stream);
 
 /* EGNN.forward (models/layers/egnn_new.py:192-205) on the canonical dense edge list of
  * en_dynamics.py:124-143.  h_in [B*N,in_node_nf], x_in [B*N,3] -> h_out [B*N,in_node_nf], x_out. */

@@ -179,7 +179,15 @@ static void equiv_forward(const hdo_config* c, const equiv_w* w, const float* h,
 /* ------------------------------------------------------------------------ */
 int hdo_dynamics_forward(const hdo_config* c, const float* wbuf, const float* z, const float* t,
                          const int32_t* sizes, int32_t B, int32_t N, float* eps, hdo_trace* tr) {
-  const int H = c->hidden_nf, Fi = c->in_node_nf, F = Fi - 1, D = 3 + F;
+  return hdo_dynamics_forward_ctx(c, wbuf, z, t, NULL, 0, sizes, B, N, eps, tr);
+}
+
+/* with `context` [B*N, C] appended after the time channel, unmasked (en_dynamics.py:76-79); the EGNN then has
+ * in_node_nf = F + 1 + C channels and the context / time channels are sliced off its output (:99-105) */
+int hdo_dynamics_forward_ctx(const hdo_config* c, const float* wbuf, const float* z, const float* t,
+                             const float* context, int32_t C, const int32_t* sizes, int32_t B, int32_t N,
+                             float* eps, hdo_trace* tr) {
+  const int H = c->hidden_nf, Fi = c->in_node_nf, F = Fi - 1 - C, D = 3 + F;
   const size_t BN = (size_t)B * N;
   const float* p = wbuf;
   const float* emb_w = take(&p, (int64_t)H * Fi);
@@ -199,6 +207,7 @@ int hdo_dynamics_forward(const hdo_config* c, const float* wbuf, const float* z,
       for (int d = 0; d < 3; ++d) x[r * 3 + d] = z[r * D + d] * mk;
       for (int f = 0; f < F; ++f) hin[r * Fi + f] = z[r * D + 3 + f] * mk;
       hin[r * Fi + F] = t[b];
+      for (int k = 0; k < C; ++k) hin[r * Fi + F + 1 + k] = context[r * C + k];
     }
   memcpy(x0, x, sizeof(float) * BN * 3);
   for (size_t r = 0; r < BN; ++r) linear(h + r * H, hin + r * Fi, emb_w, emb_b, H, Fi);

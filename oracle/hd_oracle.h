@@ -66,6 +66,10 @@ typedef struct {
  * F = in_node_nf-1.  Returns 0, or 1 if the NaN guard fired. */
 int hdo_dynamics_forward(const hdo_config* c, const float* w, const float* z, const float* t,
                          const int32_t* sizes, int32_t B, int32_t N, float* eps, hdo_trace* tr);
+/* same with per-node context channels [B*N, C] appended after time (en_dynamics.py:76-79, :99-101) */
+int hdo_dynamics_forward_ctx(const hdo_config* c, const float* w, const float* z, const float* t,
+                             const float* context, int32_t C, const int32_t* sizes, int32_t B, int32_t N,
+                             float* eps, hdo_trace* tr);
 
 /* diffusion_qm9.py:181-204, :320-334 from gamma_s, gamma_t (fp32 libm):
  * out[0]=alpha_t_given_s out[1]=sigma2_t_given_s/alpha_t_given_s/sigma_t

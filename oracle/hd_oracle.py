@@ -125,11 +125,13 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def dynamics_forward(cfg: Config, w, z, t, sizes, trace=False):
-    """en_dynamics.py:49-122.  z [B,N,3+F], t [B] or [B,1], sizes [B] -> eps [B,N,3+F]."""
+def dynamics_forward(cfg: Config, w, z, t, sizes, trace=False, context=None):
+    """en_dynamics.py:49-122.  z [B,N,3+F], t [B] or [B,1], sizes [B], context [B,N,C] or None -> eps [B,N,3+F]."""
     z = np.ascontiguousarray(z, np.float32)
     B, N, D = z.shape
-    assert D == 3 + cfg.in_node_nf - 1
+    C = 0 if context is None else int(np.asarray(context).shape[-1])
+    ctx = None if context is None else np.ascontiguousarray(np.asarray(context, np.float32).reshape(B * N, C))
+    assert D == 3 + cfg.in_node_nf - 1 - C
     t = np.ascontiguousarray(np.asarray(t, np.float32).reshape(-1))
     if t.size == 1:
         t = np.full(B, t[0], np.float32)
@@ -142,8 +144,8 @@ def dynamics_forward(cfg: Config, w, z, t, sizes, trace=False):
         shp = dict(h_embed=H, h_gcl0=H, h_gcl1=H, x_block0=3, h_final=Fi, x_final=3)
         bufs = {k: np.zeros((B * N, v), np.float32) for k, v in shp.items()}
         tr = Trace(*[_p(bufs[k]).value for k, _ in Trace._fields_])
-    nan = lib().hdo_dynamics_forward(ctypes.byref(cfg), _p(w), _p(z), _p(t), _p(sizes), B, N, _p(eps),
-                                     ctypes.byref(tr) if tr is not None else None)
+    nan = lib().hdo_dynamics_forward_ctx(ctypes.byref(cfg), _p(w), _p(z), _p(t), _p(ctx) if ctx is not None else None,
+                                         C, _p(sizes), B, N, _p(eps), ctypes.byref(tr) if tr is not None else None)
     return (eps, bufs, nan) if trace else eps
 
 

@@ -83,7 +83,7 @@ class FixedNodes(nn.Module):
         return list(self.sizes)
 
 
-def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned"):
+def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned", context_node_nf=0):
     _install_stubs()
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -94,6 +94,7 @@ def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned"):
 
     cfg = to_attr(yaml.safe_load(open(os.path.join(REF, "conf/model/ddpmgblur.yaml")))["cfg"])
     cfg.dynamics.n_layers = n_layers
+    cfg.dynamics.context_node_nf = context_node_nf
     cfg.timesteps = timesteps
     cfg.noise_schedule = noise_schedule
     if noise_schedule != "learned":
@@ -222,6 +223,61 @@ def case_sample(name, n_layers, T, sizes, seed, noise_schedule="learned"):
           "z_traj absmax", float(np.abs(np.stack(zs)).max()))
 
 
+def case_context(name="context_l1", n_layers=1, T=6, sizes=(6, 9, 2), seed=3, context=0.7):
+    """Conditioned sampling (diffusion_qm9.py:351-352, en_dynamics.py:76-79,99-101): one forward and a short chain."""
+    model = make_reference(n_layers, T, context_node_nf=1)
+    sizes = list(sizes)
+    model.nodes_dist = FixedNodes(sizes)
+    B, N = len(sizes), max(sizes)
+    g = torch.Generator().manual_seed(seed)
+    node_mask, edge_mask = masks_for(sizes, N)
+    z = torch.randn(B, N, 11, generator=g) * node_mask
+    nm = node_mask.float()
+    z[..., :3] -= (z[..., :3].sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
+    t = torch.rand(B, 1, generator=g)
+    ctx = torch.zeros(B, N, 1) + context
+    with torch.no_grad():
+        eps = model.dynamics._forward(t, z, node_mask, edge_mask, ctx, None)
+    draws, gam, zs = [], [], []
+    real_randn = torch.randn
+
+    def rec_randn(*a, **k):
+        v = real_randn(*a, **k)
+        draws.append(v.clone().numpy())
+        return v
+
+    h = model.gamma.register_forward_hook(
+        lambda m, i, o: gam.append((i[0].detach().clone().numpy(), o.detach().clone().numpy())))
+    real_step = model.sample_p_zs_given_zt
+
+    def rec_step(*a, **k):
+        v = real_step(*a, **k)
+        zs.append(v.clone().numpy())
+        return v
+
+    model.sample_p_zs_given_zt = rec_step
+    torch.manual_seed(seed)
+    torch.randn = rec_randn
+    try:
+        res = model.sample(B, torch.device("cpu"), context=context)
+    finally:
+        torch.randn = real_randn
+    h.remove()
+    x = np.zeros((B, N, 3), np.float32)
+    hh = np.zeros((B, N, 8), np.float32)
+    for i, r in enumerate(res):
+        x[i, :sizes[i]] = r["x"].numpy()
+        hh[i, :sizes[i]] = r["h"].numpy()
+        assert r["context"].shape == (sizes[i], 1)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), z=z.numpy(), t=t.numpy(), eps=eps.numpy(),
+                        context=np.float32(context), randn_x=np.stack(draws[0::2]), randn_h=np.stack(draws[1::2]),
+                        gamma_in=np.stack([g_[0][:, 0] for g_ in gam]), gamma_out=np.stack([g_[1][:, 0] for g_ in gam]),
+                        z_traj=np.stack(zs).astype(np.float32), x=x, h=hh, sizes=np.array(sizes, np.int32),
+                        T=np.int32(T), n_layers=np.int32(n_layers), weight_seed=np.int32(2022),
+                        sample_seed=np.int32(seed))
+    print(name, "eps absmax", float(eps.abs().max()), "x absmax", float(np.abs(x).max()))
+
+
 def case_gamma():
     model = make_reference(1, 1000)
     t = torch.linspace(0, 1, 41).view(-1, 1)
@@ -260,5 +316,6 @@ if __name__ == "__main__":
     case_sample("sample_c1", n_layers=6, T=50, sizes=[20, 20, 20, 20], seed=0)
     case_sample("sample_ragged_l9", n_layers=9, T=20, sizes=[10, 6, 9], seed=1)
     case_sample("sample_poly_l1", n_layers=1, T=10, sizes=[4, 8], seed=2, noise_schedule="polynomial_2")
+    case_context()
     case_gamma()
     case_nodes_dist()

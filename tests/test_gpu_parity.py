@@ -218,3 +218,31 @@ def test_full_chain_matches_reference_fixture(models, engine):
                                        g["gamma_out"][2 * k], g["gamma_out"][2 * k + 1])
         scale = tol if engine != "fast" else 0.2
         assert rel(z, g["z_traj"][T - 1]) < scale, name
+
+
+# ------------------------------------------------------------------------------------------------
+# conditioned sampling (context channels appended after time): forward and a short chain vs the reference fixture
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ctx_model(tmp_path_factory):
+    return make_model(tmp_path_factory.mktemp("ctx"), 1, timesteps=6, device=dev(), context_node_nf=1)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_context_forward_and_chain_match_reference_fixture(ctx_model, engine):
+    g = np.load(os.path.join(GOLDEN, "context_l1.npz"))
+    use(ctx_model, engine)
+    sizes, T = g["sizes"], int(g["T"])
+    B, N, _ = g["z"].shape
+    ctx = torch.full((B, N, 1), float(g["context"]), device=dev())
+    d_sizes = cuda(sizes, torch.int32)
+    eps = ctx_model.dynamics.forward_sizes(cuda(g["t"]), cuda(g["z"]), d_sizes, context=ctx)
+    assert rel(eps.cpu().numpy(), g["eps"]) < FWD_TOL[engine]
+    z = masked_cog_noise(g["randn_x"][0], g["randn_h"][0], sizes)
+    for k in range(T):
+        s = T - 1 - k
+        t = np.full(B, np.float32(s + 1) / np.float32(T), np.float32)
+        eps = ctx_model.dynamics.forward_sizes(cuda(t), cuda(z), d_sizes, context=ctx)
+        z, _ = reverse_step_native(ctx_model, z, eps, g["randn_x"][k + 1], g["randn_h"][k + 1], sizes,
+                                   g["gamma_out"][2 * k], g["gamma_out"][2 * k + 1])
+    assert rel(z, g["z_traj"][T - 1]) < (1e-4 if engine != "fast" else 0.2)

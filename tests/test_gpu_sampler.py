@@ -265,3 +265,32 @@ def test_full_t1000_chain_strict_tracks_fp32_engine(tmp_path):
         assert np.isfinite(out[engine][0]).all() and np.isfinite(out[engine][1]).all()
     assert rel(out["strict"][0], out["fp32"][0]) < 5e-4
     assert rel(out["strict"][1], out["fp32"][1]) < 5e-4
+
+
+def test_conditioned_sample_api(tmp_path):
+    """sample(context=c) / sample_batches(context_range=[...]) (diffusion_qm9.py:351-352, :390-392, :431-432):
+    a 'context' entry per molecule, graph-replayed loop == eager loop with the context buffer bound."""
+    model = make_model(tmp_path, 1, timesteps=12, device=dev(), engine="strict", context_node_nf=1)
+    torch.manual_seed(3)
+    res = model.sample(5, dev(), context=0.25)
+    assert len(res) == 5
+    for r in res:
+        n = r["x"].shape[0]
+        assert r["h"].shape == (n, 8) and r["context"].shape == (n, 1) and torch.all(r["context"] == 0.25)
+        assert torch.isfinite(r["x"]).all()
+    sizes = [7, 3, 9]
+    torch.manual_seed(4)
+    xa, ha = model.sample_padded(sizes, dev(), context=torch.full((3, 9, 1), 0.25))
+    torch.manual_seed(4)
+    xb, hb = model.sample_padded(sizes, dev(), context=torch.full((3, 9, 1), -1.5))
+    assert not torch.equal(xa, xb)                      # the condition reaches the network
+    model.use_cuda_graph = False
+    model._loops = {}
+    torch.manual_seed(4)
+    xc, hc = model.sample_padded(sizes, dev(), context=torch.full((3, 9, 1), 0.25))
+    assert torch.equal(xa, xc) and torch.equal(ha, hc)  # replayed graph == eager loop
+    out, names = model.sample_batches(2, 3, dev(), context_range=[0.1, 0.9])
+    assert len(out) == 6 and names == []
+    assert [float(r["context"][0, 0]) for r in out] == pytest.approx([0.1, 0.1, 0.9, 0.9, 0.1, 0.1])
+    with pytest.raises(ValueError):
+        model.sample_padded(sizes, dev())               # conditioned model without a context

@@ -138,11 +138,18 @@ def test_product_path_fails_loudly_without_cuda(tmp_path):
         model.phi(torch.zeros(1, 4, 11), torch.zeros(1, 1), nm, em, None)
 
 
+def _cpu_guard():
+    raise ValueError("no CUDA device in this test environment")
+
+
 def test_unsupported_options_raise(tmp_path):
     from hierdiff_b200 import EGNN, EGNN_dynamics_QM9
     with pytest.raises(NotImplementedError):
         EGNN(9, 1, 256, sin_embedding=True)
     with pytest.raises(NotImplementedError):
         EGNN_dynamics_QM9(9, 0, 3, mode="gnn_dynamics")
-    with pytest.raises(NotImplementedError):
-        EGNN_dynamics_QM9(9, 2, 3)
+    dyn = EGNN_dynamics_QM9(9, 2, 3, hidden_nf=256)     # context conditioning is built: 9 + 2 input channels
+    assert dyn.egnn.embedding.weight.shape == (256, 11) and dyn.egnn.embedding_out.weight.shape == (11, 256)
+    with pytest.raises(ValueError):                     # ... and refuses a call without its context
+        dyn.forward_sizes(torch.zeros(1), torch.zeros(1, 2, 11).cuda() if torch.cuda.is_available()
+                          else _cpu_guard(), torch.ones(1, dtype=torch.int32))

@@ -138,3 +138,14 @@ def test_torch_port_matches_reference(golden_dir, name):
     eps = port.dynamics(t.view(-1, 1), z, nm, em)
     err = np.abs(eps.numpy() - g["eps"]).max() / np.abs(g["eps"]).max()
     assert err < 2e-6, err
+
+
+def test_context_forward_matches_reference(golden_dir):
+    """Conditioned dynamics (en_dynamics.py:76-79, :99-101): oracle vs the reference fixture."""
+    g = np.load(os.path.join(golden_dir, "context_l1.npz"))
+    cfg = O.make_config(int(g["n_layers"]), in_node_nf=10)
+    w = O.flatten_weights(cfg, fill_state_dict(O.egnn_shapes(cfg)))
+    B, N, _ = g["z"].shape
+    ctx = np.full((B, N, 1), g["context"], np.float32)
+    eps = O.dynamics_forward(cfg, w, g["z"], g["t"], g["sizes"], context=ctx)
+    assert rel(eps, g["eps"]) < 1e-5
