@@ -4,15 +4,17 @@
 //
 //   rows     : the real (i,j) node pairs of every molecule, j padded to a multiple of 8 per receiver i;
 //              every CTA owns a contiguous range of whole receivers (no cross-CTA reduction, no atomics)
-//   producer : 4 warps build the MMA A operand on the fly, m1_ij = SiLU(A_i + B_j + r_ij*wr + d0_ij*wd)
+//   producer : 8 warps build the MMA A operand on the fly, m1_ij = SiLU(A_i + B_j + r_ij*wr + d0_ij*wd)
 //              (layer 1 of the edge MLP split per node), as bf16 (hi [+ lo]) core matrices in a
-//              shared-memory ring, K = 32 per stage
+//              shared-memory ring, K = 64 per stage (two stages, 64 KB)
 //   MMA      : 1 thread issues tcgen05.mma (kind::f16, M=128 per CTA, N=256, K=16) against W2 resident in
 //              shared memory; strict mode runs 3 passes (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM
 //              accumulator; cta_group::2 pairs two SMs so each holds one 128-row half of W2 (hi+lo = 128 KB)
-//   epilogue : 4 warps read the accumulator from TMEM (thread = edge row): + b2, SiLU, attention / coord
-//              dot product, mask, then a shuffle transpose-reduction over the 8 rows of a group and a
-//              per-receiver running sum -> agg_i (GCL) or x_i + sum_j trans_ij (EquivariantUpdate)
+//   epilogue : 8 warps read the accumulator from TMEM (thread = edge row, half of the columns): + b2, SiLU,
+//              attention / coord dot product (halves exchanged through shared memory), mask, then a shuffle
+//              transpose-reduction over the 8 rows of a group and a per-receiver running sum -> agg_i (GCL) or
+//              x_i + sum_j trans_ij (EquivariantUpdate)
+//   metadata : 1 warp prepares the row descriptors (receiver, sender, |x_i-x_j|^2, unit vector, flags) of tile t+1
 //
 // Accumulators are double buffered in TMEM (2 x 256 columns), so tile t's epilogue overlaps tile t+1's MMAs
 // and tile t+2's operand generation.
