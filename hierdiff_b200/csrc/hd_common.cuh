@@ -52,6 +52,12 @@ struct SubLayer {
   int64_t b2;     // [H]
   int64_t wa;     // [H]      : att_mlp.0.weight (GCL) or coord_mlp.4.weight (equiv)
   int64_t ba;     // [1] (+pad): att_mlp.0.bias (GCL) or 0
+  // tensor-core engines evaluate SiLU(v) = v / (1 + 2^t) on t = -log2(e) * v directly: these copies carry the factor,
+  // so the kernels save the multiply in front of every ex2 (the A|B pre-projection image w1ab_* is scaled likewise)
+  int64_t b1s;    // [2H]     : -log2(e) * [b1 | 0]
+  int64_t wrs;    // [H]      : -log2(e) * wr
+  int64_t wds;    // [H]      : -log2(e) * wd
+  int64_t b2s;    // [H]      : -log2(e) * b2
   int64_t v1T;    // [2H][H]  : GCL only, node_mlp.0 transposed ([h | agg] input order)
   int64_t c1;     // [H]
   int64_t v2T;    // [H][H]

@@ -101,6 +101,10 @@ bool make_layout(const hd_config& c, Layout* out) {
       S.b2 = put(H * 4);
       S.wa = put(H * 4);
       S.ba = put(16);
+      S.b1s = put(2 * H * 4);
+      S.wrs = put(H * 4);
+      S.wds = put(H * 4);
+      S.b2s = put(H * 4);
       if (S.is_gcl) {
         S.v1T = put((int64_t)2 * H * H * 4);
         S.c1 = put(H * 4);
@@ -174,14 +178,19 @@ __global__ void copy_k(const float* __restrict__ src, int n, float* __restrict__
   int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o < n) dst[o] = src ? src[o] : 0.f;
 }
+// dst[o] = scale * src[o]
+__global__ void scale_k(const float* __restrict__ src, int n, float scale, float* __restrict__ dst) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < n) dst[o] = scale * src[o];
+}
 // bf16 hi/lo operand image of rows [row0, row0+rows) x K columns [col0, col0+K) of src (ld):
 // img[kg][r][e] (kg < K/8, r < rows, e < 8)
 __global__ void image_k(const float* __restrict__ src, int ld, int row0, int col0, int rows, int K,
-                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float scale = 1.0f) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * K) return;
   int e = idx & 7, r = (idx >> 3) % rows, kg = (idx >> 3) / rows;
-  float v = src[(int64_t)(row0 + r) * ld + col0 + kg * 8 + e];
+  float v = scale * src[(int64_t)(row0 + r) * ld + col0 + kg * 8 + e];
   __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[idx] = h;
   lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -189,6 +198,7 @@ __global__ void image_k(const float* __restrict__ src, int ld, int row0, int col
 
 int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, cudaStream_t st) {
   const int T = 256;
+  const float NEG_LOG2E = -1.4426950408889634f;
   auto grid = [&](int64_t n) { return (unsigned)((n + T - 1) / T); };
   auto F = [&](int64_t off) { return reinterpret_cast<float*>(P + off); };
   auto BF = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(P + off); };
@@ -221,8 +231,13 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
       const int64_t o = (int64_t)t * 128 * H;
       const int part = t / (H / 128), row0 = (t % (H / 128)) * 128;
       image_k<<<grid(128 * H), T, 0, st>>>(w + S.s_w1, ld1, row0, part * H, 128, H, BF(S.w1ab_hi) + o,
-                                           BF(S.w1ab_lo) + o);
+                                           BF(S.w1ab_lo) + o, NEG_LOG2E);
     }
+    // scaled fp32 copies for the tensor-core engines (stream order: after the unscaled images above)
+    scale_k<<<grid(2 * H), T, 0, st>>>(F(S.b1), 2 * H, NEG_LOG2E, F(S.b1s));
+    scale_k<<<grid(H), T, 0, st>>>(F(S.wr), H, NEG_LOG2E, F(S.wrs));
+    scale_k<<<grid(H), T, 0, st>>>(F(S.wd), H, NEG_LOG2E, F(S.wds));
+    scale_k<<<grid(H), T, 0, st>>>(F(S.b2), H, NEG_LOG2E, F(S.b2s));
     if (S.is_gcl) {
       transpose_k<<<grid(2 * H * H), T, 0, st>>>(w + S.s_v1, 2 * H, 0, H, 2 * H, F(S.v1T), H, 0);
       copy_k<<<grid(H), T, 0, st>>>(w + S.s_c1, H, F(S.c1));

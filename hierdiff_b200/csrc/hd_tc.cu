@@ -126,17 +126,25 @@ __device__ __forceinline__ int align_recv(const int* row_off, const int32_t* siz
   return row_off[b] + ((local + npad - 1) / npad) * npad;
 }
 
+// SiLU in the scaled domain the kernel works in.  Operands arrive as t = -log2(e) * v (the factor is folded into the
+// packed weights, hd_layout.cu), so  SiLU(v) = v / (1 + 2^t) = -ln2 * t / (1 + 2^t).
+//   strict: returns t / (1 + 2^t)            = SiLU(v) / K_OUT, K_OUT = -ln 2       (ex2.approx, rcp.approx, ~2 ulp)
+//   fast  : returns c*t * (1 + tanh(c*t)), c = -ln2 / 2   = SiLU(v) / K_OUT, K_OUT = -1 / ln 2... see silu_kout()
 template <bool STRICT>
-__device__ __forceinline__ float silu_edge(float v) {
+__device__ __forceinline__ float silu_scaled(float t) {
   if constexpr (STRICT) {
-    // v * 1/(1+exp(-v)) with ex2.approx / rcp.approx (each ~1-2 ulp)
-    const float e = ptx::ex2_approx(-1.4426950408889634f * v);
-    return v * ptx::rcp_approx(1.0f + e);
+    return t * ptx::rcp_approx(1.0f + ptx::ex2_approx(t));
   } else {
-    const float hv = 0.5f * v;
-    return fmaf(hv, ptx::tanh_approx(hv), hv);
+    const float hv = -0.34657359027997264f * t;   // v / 2
+    return fmaf(hv, ptx::tanh_approx(hv), hv);    // = SiLU(v)
   }
 }
+// SiLU(v) = silu_kout() * silu_scaled(t)
+template <bool STRICT>
+__host__ __device__ constexpr float silu_kout() { return STRICT ? -0.6931471805599453f : 1.0f; }
+// t2 = -log2(e) * (W2 . SiLU + b2) = silu_kacc() * (W2 . silu_scaled) + b2s
+template <bool STRICT>
+__host__ __device__ constexpr float silu_kacc() { return STRICT ? 1.0f : -1.4426950408889634f; }
 
 template <bool GCL, bool STRICT, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
@@ -287,20 +295,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) m[k] = pre[k];
 #else
+      // pre[] is t = -log2(e) * (A_i + B_j + r*wr + d*wd): A|B, wr, wd carry the factor (hd_layout.cu)
       if constexpr (STRICT) {
         float e[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(-1.4426950408889634f * pre[k]);
+        for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(pre[k]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) e[k] = ptx::rcp_approx(1.0f + e[k]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];
+        for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];            // SiLU / (-ln 2)
       } else {
-        float th[8];
+        float hv[8], th[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(0.5f * pre[k]);
+        for (int k = 0; k < 8; ++k) hv[k] = -0.34657359027997264f * pre[k];   // v / 2
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaf(0.5f * pre[k], th[k], 0.5f * pre[k]);
+        for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(hv[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaf(hv[k], th[k], hv[k]);        // SiLU
       }
 #endif
 #pragma unroll
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     const float ba = GCL ? p.ba[0] : 0.f;
     auto flush = [&]() {
       if (cur_recv < 0) return;
-      if (GCL) p.out[(int64_t)cur_recv * H + etid] = carry / p.norm_div;
+      if (GCL) p.out[(int64_t)cur_recv * H + etid] = (silu_kout<STRICT>() * carry) / p.norm_div;
       else if (etid < 3) p.out[(int64_t)cur_recv * 3 + etid] = p.x[(int64_t)cur_recv * 3 + etid] + carry / p.norm_div;
     };
     HD_T0();
@@ -427,8 +438,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 #ifdef HD_EXP_NO_EPI_SILU
           const float m0 = v[4 * k4 + 0] + bb.x, m1 = v[4 * k4 + 1] + bb.y, m2 = v[4 * k4 + 2] + bb.z, m3 = v[4 * k4 + 3] + bb.w;
 #else
-          const float m0 = silu_edge<STRICT>(v[4 * k4 + 0] + bb.x), m1 = silu_edge<STRICT>(v[4 * k4 + 1] + bb.y);
-          const float m2 = silu_edge<STRICT>(v[4 * k4 + 2] + bb.z), m3 = silu_edge<STRICT>(v[4 * k4 + 3] + bb.w);
+          // bb = -log2(e) * b2; KACC undoes the producer's output scale: t2 = -log2(e) * (W2 . SiLU + b2)
+          constexpr float KACC = silu_kacc<STRICT>();
+          const float m0 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 0], bb.x));
+          const float m1 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 1], bb.y));
+          const float m2 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 2], bb.z));
+          const float m3 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 3], bb.w));
 #endif
           dot = fmaf(m0, ww.x, dot);
           dot = fmaf(m1, ww.y, dot);
@@ -443,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       s_dot[half * TILE_M + 32 * q + lane] = dot;
       ptx::named_bar_sync(4, EPI_THREADS);
       HD_ACC(1, 2, etid == 0);   // exchange barrier
-      dot = s_dot[32 * q + lane] + s_dot[TILE_M + 32 * q + lane];
+      dot = silu_kout<STRICT>() * (s_dot[32 * q + lane] + s_dot[TILE_M + 32 * q + lane]);   // back to the true scale
       if (GCL) {
         ptx::tmem_wait_st();
         float att = 1.0f;
@@ -737,11 +752,11 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   p.row_off = reinterpret_cast<const int32_t*>(c.ws + c.W.row_off);
   p.w_hi = c.packed + S.w2_hi;
   p.w_lo = c.packed + S.w2_lo;
-  p.b2 = F(S.b2);
+  p.b2 = F(S.b2s);   // the -log2(e)-scaled copies (silu_scaled)
   p.wa = F(S.wa);
   p.ba = F(S.ba);
-  p.wr = F(S.wr);
-  p.wd = F(S.wd);
+  p.wr = F(S.wrs);
+  p.wd = F(S.wds);
   p.out = out;
   p.B = c.B;
   p.N = c.N;
@@ -763,11 +778,12 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
               const void* w_lo, int n_out, int tile_n, const float* bias, float* Y, int ldy, int mode,
               const float* resid, bool strict);
 
-// A = h W1a^T + b1 ; B = h W1b^T  (packed b1 image is [b1 | 0], so the bias lands on the A half only)
+// A = -log2(e) (h W1a^T + b1) ; B = -log2(e) h W1b^T  (scaled images: silu_scaled; the bias image is [b1 | 0], so the
+// bias lands on the A half only)
 static int preproject(const FwdCtx& c, const SubLayer& S, const float* h, bool strict) {
   float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
   return linear_tc(c, h, H, H, nullptr, 0, 0, c.packed + S.w1ab_hi, c.packed + S.w1ab_lo, 2 * H, 128,
-                   reinterpret_cast<const float*>(c.packed + S.b1), ab, 2 * H, 3, nullptr, strict);
+                   reinterpret_cast<const float*>(c.packed + S.b1s), ab, 2 * H, 3, nullptr, strict);
 }
 
 int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine) {
