@@ -171,7 +171,9 @@ class EGNN(nn.Module):
         if k not in self._ws:
             nbytes = native.lib().hd_workspace_bytes(self.hd_config(), B, N)
             # keep every shape's buffer: captured CUDA graphs hold raw pointers into them
-            self._ws[k] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            # zero-filled once: rows of padded nodes in `agg` are never written by the edge kernel (it only visits
+            # real receivers) but are read as GEMM operand rows (their outputs are masked); they must stay finite
+            self._ws[k] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         return self._ws[k]
 
     def engine_id(self, engine=None):

@@ -91,7 +91,8 @@ HD_API int64_t hd_weight_count(const hd_config* cfg);
 HD_API int64_t hd_packed_bytes(const hd_config* cfg);
 HD_API int32_t hd_pack_weights(const hd_config* cfg, const float* w_flat, void* packed, hd_stream_t stream);
 
-/* Scratch bytes one forward needs for a padded batch of B molecules x N nodes. */
+/* Scratch bytes one forward needs for a padded batch of B molecules x N nodes.  Zero-fill the buffer once after
+ * allocating it: rows that belong to padded nodes are read as (masked) GEMM operand rows but never written. */
 HD_API int64_t hd_workspace_bytes(const hd_config* cfg, int32_t B, int32_t N);
 
 /* EGNN_dynamics_QM9._forward (models/module/en_dynamics.py:49-122) for mode 'egnn_dynamics',
