@@ -335,21 +335,33 @@ static int sub_equiv(const FwdCtx& c, int si, const float* h, const float* x, co
   return tc_equiv(c, si, h, x, x0, xo, engine);
 }
 
-// EGNN blocks (egnn_new.py:198-199, :139-152) on ws.h / ws.x; returns the buffer holding the final x
-static int run_blocks(const FwdCtx& c, int engine, float** x_final) {
+// EGNN blocks (egnn_new.py:198-199, :139-152) on ws.h / ws.x; returns the buffers holding the final h and x
+static int run_blocks(const FwdCtx& c, int engine, float** h_final, float** x_final) {
   float* h = reinterpret_cast<float*>(c.ws + c.W.h);
+  float* h2 = reinterpret_cast<float*>(c.ws + c.W.h2);
   float* x = reinterpret_cast<float*>(c.ws + c.W.x);
   float* x2 = reinterpret_cast<float*>(c.ws + c.W.x2);
   const float* x0 = reinterpret_cast<const float*>(c.ws + c.W.x0);
   int si = 0, rc;
+  c.ab_ready = false;
   for (int l = 0; l < c.cfg->n_layers; ++l) {
-    for (int s = 0; s < c.cfg->inv_sublayers; ++s)
-      if ((rc = sub_gcl(c, si++, h, x, x0, engine))) return rc;
+    for (int s = 0; s < c.cfg->inv_sublayers; ++s) {
+      if (engine != HD_ENGINE_FP32 && c.L->subs[si].fuse_next) {
+        // tensor-core engines: node_mlp.2 and the next sub-layer's pre-projection share a launch; h ping-pongs
+        if ((rc = tc_gcl_fused(c, si++, h, h2, x, x0, engine))) return rc;
+        float* tmp = h;
+        h = h2;
+        h2 = tmp;
+      } else if ((rc = sub_gcl(c, si++, h, x, x0, engine))) {
+        return rc;
+      }
+    }
     if ((rc = sub_equiv(c, si++, h, x, x0, x2, engine))) return rc;
     float* tmp = x;
     x = x2;
     x2 = tmp;
   }
+  *h_final = h;
   *x_final = x;
   return HD_OK;
 }
@@ -433,9 +445,9 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
   HD_CHECK_CUDA(launch_pdl(embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.hin), Fi,
                           PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h)));
   count_launch();
-  float* xf = nullptr;
-  if ((rc = run_blocks(c, engine, &xf))) return rc;
-  HD_CHECK_CUDA(launch_pdl(out_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.h), PF(L.out_w),
+  float *hf = nullptr, *xf = nullptr;
+  if ((rc = run_blocks(c, engine, &hf, &xf))) return rc;
+  HD_CHECK_CUDA(launch_pdl(out_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)hf, PF(L.out_w),
                           PF(L.out_b), Fi, sizes, N, WF(c.W.hout)));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(vel_k, dim3((unsigned)((BN * D + 255) / 256)), dim3(256), 0, c.stream, (const float*)xf,
@@ -469,9 +481,9 @@ HD_API int32_t hd_egnn_forward(const hd_config* cfg, const void* packed, const f
   HD_CHECK_CUDA(cudaMemcpyAsync(WF(c.W.x0), x_in, BN * 3 * 4, cudaMemcpyDeviceToDevice, c.stream));
   embed_k<<<(unsigned)BN, 256, 0, c.stream>>>(h_in, Fi, PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h));
   HD_CHECK_LAUNCH();
-  float* xf = nullptr;
-  if ((rc = run_blocks(c, engine, &xf))) return rc;
-  out_k<<<(unsigned)BN, 256, 0, c.stream>>>(WF(c.W.h), PF(L.out_w), PF(L.out_b), Fi, sizes, N, h_out);
+  float *hf = nullptr, *xf = nullptr;
+  if ((rc = run_blocks(c, engine, &hf, &xf))) return rc;
+  out_k<<<(unsigned)BN, 256, 0, c.stream>>>(hf, PF(L.out_w), PF(L.out_b), Fi, sizes, N, h_out);
   HD_CHECK_LAUNCH();
   HD_CHECK_CUDA(cudaMemcpyAsync(x_out, xf, BN * 3 * 4, cudaMemcpyDeviceToDevice, c.stream));
   return HD_OK;

@@ -69,10 +69,17 @@ struct SubLayer {
   int64_t w1ab_hi, w1ab_lo;    // [2H out][H k] node pre-projection (4 tiles)
   int64_t v1_hi, v1_lo;        // [H out][2H k]  (GCL) node_mlp.0 (4 tiles, K = 2H)
   int64_t v2_hi, v2_lo;        // [H out][H k]   (GCL) node_mlp.2 (4 tiles)
+  // fused launch "node_mlp.2 + next pre-projection" (GCL followed by another sub-layer of the same block), 128-row tiles:
+  int64_t v2w_hi, v2w_lo;      // [H out][H k]    node_mlp.2 again, 2 tiles
+  int64_t m_hi, m_lo;          // [2H out][2H k]  -log2(e) * [W1ab_next | W1ab_next . V2]: applied to [h | hid] it gives the
+                               //                 next sub-layer's A|B of h' = h + V2 hid + c2 without waiting for h'
+  int64_t bm;                  // [2H] fp32       -log2(e) * ([b1_next | 0] + W1ab_next . c2)
+  bool fuse_next;              // the three fields above are populated
 };
 
 struct Layout {
   int64_t s_emb_w, s_emb_b, s_out_w, s_out_b;  // flat offsets
+  int64_t fuse_tmp;  // [2H][2H] fp32 scratch of pack_weights
   int64_t emb_wT;  // [Fi][H]
   int64_t emb_b;   // [H]
   int64_t out_w;   // [Fi][H] (as in the state_dict)
@@ -93,6 +100,7 @@ struct Workspace {
   int64_t ab;     // [BN][2H]   node pre-projection: A_i (bias folded) | B_j
   int64_t agg;    // [BN][H]
   int64_t hid;    // [BN][H]
+  int64_t h2;     // [BN][H]    ping-pong partner of h (the fused node launch must not update h in place)
   int64_t x;      // [BN][3]
   int64_t x2;     // [BN][3]    ping-pong for the coordinate update
   int64_t x0;     // [BN][3]    EGNN-entry coordinates
@@ -159,6 +167,7 @@ struct FwdCtx {
   int B, N;
   cudaStream_t stream;
   mutable bool planned = false;  // ws.row_off holds the edge-row prefix for `sizes`
+  mutable bool ab_ready = false; // ws.ab already holds the next sub-layer's A|B operands (fused node launch)
   bool x_prezeroed = false;      // padded rows of ws.x / ws.x2 are already 0 (hd_dynamics_forward): the coordinate
                                  // update then needs no memset of its output
 };
@@ -167,6 +176,9 @@ struct FwdCtx {
 int fp32_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0);
 int fp32_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out);
 int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine);
+// same, but when `h_out` != nullptr and the sub-layer has a fused successor: h_out receives the updated features
+// (h is left untouched) and the successor's A|B operands are produced in the same launch (c.ab_ready is set)
+int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const float* x, const float* x0, int engine);
 int tc_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out, int engine);
 // edge kernel alone on ws.ab (profiling hook); output into ws.agg (GCL) / ws.x2 (equiv)
 int fp32_edge_only(const FwdCtx& c, int si, const float* x, const float* x0);

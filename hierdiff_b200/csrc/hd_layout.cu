@@ -66,6 +66,7 @@ bool make_layout(const hd_config& c, Layout* out) {
     p = align256(p + bytes);
     return r;
   };
+  L.fuse_tmp = put((int64_t)2 * H * 2 * H * 4);
   L.emb_wT = put(Fi * H * 4);
   L.emb_b = put(H * 4);
   L.out_w = put(Fi * H * 4);
@@ -122,8 +123,17 @@ bool make_layout(const hd_config& c, Layout* out) {
         S.v1_lo = put((int64_t)2 * H * H * 2);
         S.v2_hi = put((int64_t)H * H * 2);
         S.v2_lo = put((int64_t)H * H * 2);
+        // every GCL is followed by another sub-layer of its block (a GCL or the EquivariantUpdate)
+        S.fuse_next = true;
+        S.v2w_hi = put((int64_t)H * H * 2);
+        S.v2w_lo = put((int64_t)H * H * 2);
+        S.m_hi = put((int64_t)2 * H * 2 * H * 2);
+        S.m_lo = put((int64_t)2 * H * 2 * H * 2);
+        S.bm = put(2 * H * 4);
       } else {
         S.v1_hi = S.v1_lo = S.v2_hi = S.v2_lo = -1;
+        S.fuse_next = false;
+        S.v2w_hi = S.v2w_lo = S.m_hi = S.m_lo = S.bm = -1;
       }
       L.subs.push_back(S);
     }
@@ -146,6 +156,7 @@ Workspace make_workspace(const hd_config& c, int B, int N) {
   W.ab = put(BN * 2 * H * 4);
   W.agg = put(BN * H * 4);
   W.hid = put(BN * H * 4);
+  W.h2 = put(BN * H * 4);
   W.x = put(BN * 3 * 4);
   W.x2 = put(BN * 3 * 4);
   W.x0 = put(BN * 3 * 4);
@@ -183,6 +194,25 @@ __global__ void scale_k(const float* __restrict__ src, int n, float scale, float
   int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o < n) dst[o] = scale * src[o];
 }
+// Fused pre-projection of the sub-layer that follows a GCL:  A|B(h') with h' = h + V2 hid + c2 equals
+//   [h | hid] . [W1ab | W1ab V2]^T + (b1ab + W1ab c2).
+// tmp[o][k] (o < 2H outputs, k < 2H inputs): k < H -> W1ab[o][k], k >= H -> sum_j W1ab[o][j] * V2[j][k-H];  bm[o] likewise.
+// W1ab[o][j] = W1n[o % H][(o / H) * H + j] (outputs 0..H-1 act on h_i, H..2H-1 on h_j); fp64 accumulation.
+__global__ void fuse_k(const float* __restrict__ w1n, int ld1, const float* __restrict__ b1n,
+                       const float* __restrict__ v2, const float* __restrict__ c2, float* __restrict__ tmp,
+                       float* __restrict__ bm, float scale) {
+  const int o = blockIdx.x, k = threadIdx.x;   // grid 2H, block H
+  const float* wrow = w1n + (int64_t)(o % H) * ld1 + (o / H) * H;
+  double acc = 0.0;
+  for (int j = 0; j < H; ++j) acc += (double)wrow[j] * (double)v2[(int64_t)j * H + k];
+  tmp[(int64_t)o * 2 * H + k] = wrow[k];
+  tmp[(int64_t)o * 2 * H + H + k] = (float)acc;
+  if (k == 0) {
+    double b = o < H ? (double)b1n[o] : 0.0;
+    for (int j = 0; j < H; ++j) b += (double)wrow[j] * (double)c2[j];
+    bm[o] = scale * (float)b;
+  }
+}
 // bf16 hi/lo operand image of rows [row0, row0+rows) x K columns [col0, col0+K) of src (ld):
 // img[kg][r][e] (kg < K/8, r < rows, e < 8)
 __global__ void image_k(const float* __restrict__ src, int ld, int row0, int col0, int rows, int K,
@@ -207,7 +237,8 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
   copy_k<<<grid(H), T, 0, st>>>(w + L.s_emb_b, H, F(L.emb_b));
   copy_k<<<grid(Fi * H), T, 0, st>>>(w + L.s_out_w, Fi * H, F(L.out_w));
   copy_k<<<grid(Fi), T, 0, st>>>(w + L.s_out_b, Fi, F(L.out_b));
-  for (const SubLayer& S : L.subs) {
+  for (size_t si = 0; si < L.subs.size(); ++si) {
+    const SubLayer& S = L.subs[si];
     const int ld1 = 2 * H + 2;
     transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_w1, ld1, 0, H, H, F(S.w1abT), 2 * H, 0);
     transpose_k<<<grid(H * H), T, 0, st>>>(w + S.s_w1, ld1, H, H, H, F(S.w1abT), 2 * H, H);
@@ -248,6 +279,20 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
         image_k<<<grid(64 * 2 * H), T, 0, st>>>(w + S.s_v1, 2 * H, t * 64, 0, 64, 2 * H, BF(S.v1_hi) + o1,
                                                 BF(S.v1_lo) + o1);
         image_k<<<grid(64 * H), T, 0, st>>>(w + S.s_v2, H, t * 64, 0, 64, H, BF(S.v2_hi) + o2, BF(S.v2_lo) + o2);
+      }
+      if (S.fuse_next) {
+        const SubLayer& Nx = L.subs[si + 1];   // next sub-layer of the same block
+        for (int t = 0; t < H / 128; ++t) {
+          const int64_t o = (int64_t)t * 128 * H;
+          image_k<<<grid(128 * H), T, 0, st>>>(w + S.s_v2, H, t * 128, 0, 128, H, BF(S.v2w_hi) + o, BF(S.v2w_lo) + o);
+        }
+        fuse_k<<<2 * H, H, 0, st>>>(w + Nx.s_w1, ld1, w + Nx.s_b1, w + S.s_v2, w + S.s_c2, F(L.fuse_tmp), F(S.bm),
+                                    NEG_LOG2E);
+        for (int t = 0; t < 2 * H / 128; ++t) {
+          const int64_t o = (int64_t)t * 128 * 2 * H;
+          image_k<<<grid(128 * 2 * H), T, 0, st>>>(F(L.fuse_tmp), 2 * H, t * 128, 0, 128, 2 * H, BF(S.m_hi) + o,
+                                                   BF(S.m_lo) + o, NEG_LOG2E);
+        }
       }
     }
   }

@@ -91,9 +91,18 @@ __device__ __forceinline__ float silu_node(float v) {
   }
 }
 
+// Two independent GEMMs over the same row tiles may share one launch (column tiles [0, tiles_a) belong to problem a,
+// the rest to problem b): node_mlp.2 and the next sub-layer's pre-projection run side by side that way.
+struct Params2 {
+  Params a, b;
+  int tiles_a;
+};
+
 template <bool STRICT, int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
+__global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   using S = Smem<STRICT, NT>;
+  const bool second = (int)blockIdx.y >= pp.tiles_a;
+  const Params p = second ? pp.b : pp.a;
   constexpr int W_KG = S::W_KG, W_PART = S::W_PART, OT_LD = S::OT_LD, NSTG = S::NSTG;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
   float* s_bias = reinterpret_cast<float*>(smem + S::OFF_BIAS);
 
   const int K = p.K1 + p.K2, nch = K / KC, nch1 = p.K1 / KC;
-  const int row0 = blockIdx.x * TM, ct = blockIdx.y;
+  const int row0 = blockIdx.x * TM, ct = second ? (int)blockIdx.y - pp.tiles_a : (int)blockIdx.y;
   HD_STAMP(0, tid == 0);
   pdl_trigger();   // the next kernel's CTAs may be scheduled as soon as resources free up (they wait for our completion)
 
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params p) {
 }
 
 template <bool STRICT, int NT>
-static int launch(const Params& p, int n_out, cudaStream_t st) {
+static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, cudaStream_t st) {
   using S = Smem<STRICT, NT>;
   static bool configured = false;
   auto kern = linear_tc_k<STRICT, NT>;
@@ -306,25 +315,25 @@ static int launch(const Params& p, int n_out, cudaStream_t st) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  dim3 grid((p.rows + TM - 1) / TM, n_out / NT);
-  HD_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), S::TOTAL, st, p));
+  Params2 pp{};
+  pp.a = a;
+  pp.b = b ? *b : a;
+  pp.tiles_a = n_out_a / NT;
+  dim3 grid((a.rows + TM - 1) / TM, pp.tiles_a + (b ? n_out_b / NT : 0));
+  HD_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), S::TOTAL, st, pp));
   count_launch();
   return HD_OK;
+}
+template <bool STRICT, int NT>
+static int launch(const Params& p, int n_out, cudaStream_t st) {
+  return launch2<STRICT, NT>(p, n_out, nullptr, 0, st);
 }
 
 }  // namespace lin
 
-// Y = epilogue([X1 | X2] W^T + bias) on the tensor cores; W given as its bf16 hi/lo images in `tile_n`-row output
-// tiles (hd_layout.cu): tile_n = 128 for the 512-wide pre-projection, 64 for the 256-wide node_mlp layers, so that
-// every launch is a single wave of CTAs at the sampling path's batch sizes
-int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const void* w_hi,
-              const void* w_lo, int n_out, int tile_n, const float* bias, float* Y, int ldy, int mode,
-              const float* resid, bool strict) {
-  if (K1 % lin::KC || K2 % lin::KC || (tile_n != 64 && tile_n != 128) || n_out % tile_n || (ld1 & 3) || (ld2 & 3) ||
-      (ldy & 3)) {
-    set_error("linear_tc: unsupported shape K1=%d K2=%d n_out=%d tile_n=%d", K1, K2, n_out, tile_n);
-    return HD_E_INVALID;
-  }
+static lin::Params make_params(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2,
+                               const void* w_hi, const void* w_lo, const float* bias, float* Y, int ldy, int mode,
+                               const float* resid) {
   lin::Params p{};
   p.X1 = X1;
   p.X2 = X2 ? X2 : X1;
@@ -342,8 +351,33 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
   p.resid = resid ? resid : Y;
   p.sizes = c.sizes;
   p.N = c.N;
+  return p;
+}
+
+// Y = epilogue([X1 | X2] W^T + bias) on the tensor cores; W given as its bf16 hi/lo images in `tile_n`-row output
+// tiles (hd_layout.cu): tile_n = 128 for the 512-wide pre-projection, 64 for the 256-wide node_mlp layers, so that
+// every launch is a single wave of CTAs at the sampling path's batch sizes
+int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2, const void* w_hi,
+              const void* w_lo, int n_out, int tile_n, const float* bias, float* Y, int ldy, int mode,
+              const float* resid, bool strict) {
+  if (K1 % lin::KC || K2 % lin::KC || (tile_n != 64 && tile_n != 128) || n_out % tile_n || (ld1 & 3) || (ld2 & 3) ||
+      (ldy & 3)) {
+    set_error("linear_tc: unsupported shape K1=%d K2=%d n_out=%d tile_n=%d", K1, K2, n_out, tile_n);
+    return HD_E_INVALID;
+  }
+  const lin::Params p = make_params(c, X1, ld1, K1, X2, ld2, K2, w_hi, w_lo, bias, Y, ldy, mode, resid);
   if (tile_n == 128) return strict ? lin::launch<true, 128>(p, n_out, c.stream) : lin::launch<false, 128>(p, n_out, c.stream);
   return strict ? lin::launch<true, 64>(p, n_out, c.stream) : lin::launch<false, 64>(p, n_out, c.stream);
+}
+
+// node_mlp.2 (+ residual, mask) -> h_out and, in the same launch, the next sub-layer's A|B pre-projection computed
+// from [h | hid] with the pre-multiplied weight image (hd_layout.cu "fused pre-projection"): both in 128-column tiles
+int linear_tc_v2_and_preproject(const FwdCtx& c, const float* hid, const float* h, float* h_out, const void* v2_hi,
+                                const void* v2_lo, const float* c2, const void* m_hi, const void* m_lo,
+                                const float* bm, float* ab, bool strict) {
+  const lin::Params a = make_params(c, hid, H, H, nullptr, 0, 0, v2_hi, v2_lo, c2, h_out, H, 2, h);
+  const lin::Params b = make_params(c, h, H, H, hid, H, H, m_hi, m_lo, bm, ab, 2 * H, 3, nullptr);
+  return strict ? lin::launch2<true, 128>(a, H, &b, 2 * H, c.stream) : lin::launch2<false, 128>(a, H, &b, 2 * H, c.stream);
 }
 
 }  // namespace hd

@@ -786,6 +786,32 @@ static int preproject(const FwdCtx& c, const SubLayer& S, const float* h, bool s
                    reinterpret_cast<const float*>(c.packed + S.b1s), ab, 2 * H, 3, nullptr, strict);
 }
 
+int linear_tc_v2_and_preproject(const FwdCtx& c, const float* hid, const float* h, float* h_out, const void* v2_hi,
+                                const void* v2_lo, const float* c2, const void* m_hi, const void* m_lo,
+                                const float* bm, float* ab, bool strict);
+
+int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const float* x, const float* x0, int engine) {
+  const SubLayer& S = c.L->subs[si];
+  auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
+  float* agg = reinterpret_cast<float*>(c.ws + c.W.agg);
+  float* hid = reinterpret_cast<float*>(c.ws + c.W.hid);
+  const bool strict = engine == HD_ENGINE_TC_STRICT;
+  int rc;
+  if (!c.ab_ready && (rc = preproject(c, S, h, strict))) return rc;
+  c.ab_ready = false;
+  if ((rc = edge_launch(c, si, x, x0, agg, engine))) return rc;
+  if ((rc = linear_tc(c, h, H, H, agg, H, H, c.packed + S.v1_hi, c.packed + S.v1_lo, H, 64, F(S.c1), hid, H, 1, nullptr,
+                      strict)))
+    return rc;
+  // node_mlp.2 -> h_out, and the successor's A|B from [h | hid] in the same launch (the edge kernel has consumed ab)
+  if ((rc = linear_tc_v2_and_preproject(c, hid, h, h_out, c.packed + S.v2w_hi, c.packed + S.v2w_lo, F(S.c2),
+                                        c.packed + S.m_hi, c.packed + S.m_lo, F(S.bm), ab, strict)))
+    return rc;
+  c.ab_ready = true;
+  return HD_OK;
+}
+
 int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine) {
   const SubLayer& S = c.L->subs[si];
   auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
@@ -806,7 +832,8 @@ int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, i
 int tc_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out, int engine) {
   const SubLayer& S = c.L->subs[si];
   int rc;
-  if ((rc = preproject(c, S, h, engine == HD_ENGINE_TC_STRICT))) return rc;
+  if (!c.ab_ready && (rc = preproject(c, S, h, engine == HD_ENGINE_TC_STRICT))) return rc;
+  c.ab_ready = false;
   return edge_launch(c, si, x, x0, x_out, engine);
 }
 
