@@ -77,6 +77,97 @@ __global__ void __launch_bounds__(256) out_k(const float* __restrict__ h, const 
   }
 }
 
+// prep_k + embed_k in one launch (the sampling path): one CTA per node row.  Block 0 also resets the NaN flag and,
+// for the tensor-core engines, builds the edge-row prefix row_off[b+1] = sum_{b' <= b} n_b' * pad8(n_b') that
+// tc::plan_k would otherwise compute in a launch of its own (row_off may be null).
+__global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z, const float* __restrict__ t,
+                                                    const float* __restrict__ context, int C,
+                                                    const int32_t* __restrict__ sizes, int B, int N, int F,
+                                                    const float* __restrict__ wT, const float* __restrict__ bias,
+                                                    float* __restrict__ x, float* __restrict__ x0,
+                                                    float* __restrict__ x2, float* __restrict__ h,
+                                                    int32_t* __restrict__ nanflag, int32_t* __restrict__ row_off) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_in[64];
+  const int D = 3 + F, Fi = F + 1 + C;
+  const int64_t r = blockIdx.x;
+  const int tid = threadIdx.x, b = (int)(r / N), i = (int)(r % N);
+  const bool real = i < sizes[b];
+  const float mk = real ? 1.f : 0.f;
+  if (r == 0 && tid < 32) {
+    if (tid == 0) *nanflag = 0;
+    if (row_off) {
+      int carry = 0;
+      if (tid == 0) row_off[0] = 0;
+      for (int base = 0; base < B; base += 32) {
+        const int bb = base + tid;
+        const int n = bb < B ? sizes[bb] : 0;
+        int v = n * ((n + 7) & ~7);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, v, o);
+          if (tid >= o) v += u;
+        }
+        if (bb < B) row_off[bb + 1] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+  }
+  if (tid < 3) {
+    const float v = z[r * D + tid] * mk;
+    x[r * 3 + tid] = v;
+    x0[r * 3 + tid] = v;
+    x2[r * 3 + tid] = 0.f;   // ping-pong buffer of the coordinate updates: padded rows stay 0
+  } else if (tid < D) {
+    s_in[tid - 3] = z[r * D + tid] * mk;
+  } else if (tid == D) {
+    s_in[F] = t[b];          // time and context are not masked (en_dynamics.py:66-79)
+  } else if (tid < D + 1 + C) {
+    s_in[F + (tid - D)] = context[r * C + (tid - D - 1)];
+  }
+  __syncthreads();
+  float v = 0.f;
+  if (real) {
+    v = bias[tid];
+    for (int f = 0; f < Fi; ++f) v = fmaf(s_in[f], wT[f * H + tid], v);
+  }
+  h[r * H + tid] = v;
+}
+
+// out_k + vel_k in one launch (the sampling path): one CTA per node row
+__global__ void __launch_bounds__(256) out_vel_k(const float* __restrict__ h, const float* __restrict__ w,
+                                                 const float* __restrict__ bias, int Fi, int F,
+                                                 const int32_t* __restrict__ sizes, int N,
+                                                 const float* __restrict__ xf, const float* __restrict__ x0,
+                                                 float* __restrict__ eps_raw, int32_t* __restrict__ nanflag) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float s_out[64];
+  const int64_t r = blockIdx.x;
+  const int tid = threadIdx.x, b = (int)(r / N), i = (int)(r % N), warp = tid >> 5, lane = tid & 31;
+  const bool real = i < sizes[b];
+  for (int f = warp; f < Fi; f += 8) {
+    float s = 0.f;
+    if (real)
+      for (int c = lane; c < H; c += 32) s = fmaf(h[r * H + c], w[f * H + c], s);
+    s = warp_sum(s);
+    if (lane == 0) s_out[f] = real ? s + bias[f] : 0.f;
+  }
+  __syncthreads();
+  const int D = 3 + F;   // the first F of the Fi output channels: time and context are sliced off (en_dynamics.py:99-105)
+  if (tid < D) {
+    float v;
+    if (tid < 3) {
+      v = (xf[r * 3 + tid] - x0[r * 3 + tid]) * (real ? 1.f : 0.f);
+      if (isnan(v)) atomicOr(nanflag, 1);
+    } else {
+      v = s_out[tid - 3];
+    }
+    eps_raw[r * D + tid] = v;
+  }
+}
+
 // en_dynamics.py:89,103-111: vel = (x_final - x)*mask, drop the time channel, NaN detection.
 __global__ void vel_k(const float* __restrict__ xf, const float* __restrict__ x0, const float* __restrict__ hout,
                       const int32_t* __restrict__ sizes, int B, int N, int F, int Fi, float* __restrict__ eps_raw,
@@ -439,19 +530,23 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
   auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
   auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   int32_t* nanflag = reinterpret_cast<int32_t*>(c.ws + c.W.nanflag);
-  HD_CHECK_CUDA(launch_pdl(prep_k, dim3((unsigned)((BN * (D + 1 + C) + 255) / 256)), dim3(256), 0, c.stream, z, t, context,
-                          C, sizes, B, N, F, WF(c.W.hin), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), nanflag));
+  if (Fi > 64 || D > 256) {
+    set_error("in_node_nf=%d too large for the fused input kernel", Fi);
+    return HD_E_INVALID;
+  }
+  int32_t* row_off = engine == HD_ENGINE_FP32 ? nullptr : reinterpret_cast<int32_t*>(c.ws + c.W.row_off);
+  if (row_off && B > 255) {
+    set_error("tensor-core engine supports at most 255 molecules per call (got %d)", B);
+    return HD_E_INVALID;
+  }
+  HD_CHECK_CUDA(launch_pdl(prep_embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, z, t, context, C, sizes, B, N, F,
+                          PF(L.emb_wT), PF(L.emb_b), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), WF(c.W.h), nanflag, row_off));
   count_launch();
-  HD_CHECK_CUDA(launch_pdl(embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)WF(c.W.hin), Fi,
-                          PF(L.emb_wT), PF(L.emb_b), sizes, N, WF(c.W.h)));
-  count_launch();
+  c.planned = row_off != nullptr;
   float *hf = nullptr, *xf = nullptr;
   if ((rc = run_blocks(c, engine, &hf, &xf))) return rc;
-  HD_CHECK_CUDA(launch_pdl(out_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)hf, PF(L.out_w),
-                          PF(L.out_b), Fi, sizes, N, WF(c.W.hout)));
-  count_launch();
-  HD_CHECK_CUDA(launch_pdl(vel_k, dim3((unsigned)((BN * D + 255) / 256)), dim3(256), 0, c.stream, (const float*)xf,
-                          (const float*)WF(c.W.x0), (const float*)WF(c.W.hout), sizes, B, N, F, Fi, WF(c.W.eps_raw),
+  HD_CHECK_CUDA(launch_pdl(out_vel_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)hf, PF(L.out_w),
+                          PF(L.out_b), Fi, F, sizes, N, (const float*)xf, (const float*)WF(c.W.x0), WF(c.W.eps_raw),
                           nanflag));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(cog_k, dim3(B), dim3(128), sizeof(float) * N * D, c.stream, (const float*)WF(c.W.eps_raw),
