@@ -100,10 +100,10 @@ def load_config(config_dir, config_name="sample", overrides=()):
 
 
 def default_model_cfg(n_layers=6, timesteps=1000, noise_schedule="learned", analyze=None, hidden_nf=256,
-                      context_node_nf=0):
+                      context_node_nf=0, pocket=False):
     """The sampler-relevant content of the shipped model config (conf/model/ddpmgblur.yaml:2-37)."""
     cfg = to_config(dict(
-        pocket=False, node_coarse_type="prop", loss_type="vlb", hcontinous=True, noise_schedule=noise_schedule,
+        pocket=pocket, node_coarse_type="prop", loss_type="vlb", hcontinous=True, noise_schedule=noise_schedule,
         timesteps=timesteps, norm_values=[1.0, 1.0, 1.0], norm_biases=[None, 0.0, 0.0], parametrization="eps",
         include_charges=True, dataset="qm9", conditioning=[], data_augmentation=False,
         pre_noise=dict(noise_schedule=noise_schedule, timesteps=timesteps, precision=1e-4),

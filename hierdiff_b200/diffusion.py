@@ -34,8 +34,6 @@ class DiffusionQM9(nn.Module):
         self.cwd = "../../../../../../"   # the reference resolves cfg.analyze from its hydra run dir (:39)
         self.cfg = cfg
         self.pocket = cfg.pocket
-        if self.pocket:
-            raise NotImplementedError("pocket-conditioned sampling (cfg.pocket) is not built yet")
         self.node_coarse_type = cfg["node_coarse_type"]
         if self.node_coarse_type == "prop":
             self.in_node_nf = 8
@@ -44,6 +42,8 @@ class DiffusionQM9(nn.Module):
         else:
             raise NotImplementedError("node_coarse_type should be prop or elem")
         cfg.dynamics["in_node_nf"] = self.in_node_nf          # the reference mutates cfg here too (:47)
+        if self.pocket:
+            self.pocket_embed = nn.Embedding(21, self.in_node_nf)   # :55-56 (kept for state_dict compatibility)
         assert cfg.loss_type in {"vlb", "l2"}
         self.loss_type = cfg.loss_type
         self.include_charges = cfg.include_charges
@@ -271,7 +271,7 @@ class DiffusionQM9(nn.Module):
     def sample(self, num_samples, device, context=None, pocket_cond=None):
         """diffusion_qm9.py:347-395: list of {'x': [n_i,3], 'h': [n_i,F]} CPU tensors."""
         if pocket_cond is not None:
-            raise NotImplementedError("pocket conditioning is not built yet")
+            self._check_pocket_cond(pocket_cond, num_samples)
         sample_n = self.nodes_dist.sample(num_samples)
         if context is not None:   # "only for global context" (:351-352): broadcast over molecules and nodes
             context = torch.zeros(num_samples, max(sample_n), 1) + torch.as_tensor(context, dtype=torch.float32).cpu()
@@ -282,12 +282,62 @@ class DiffusionQM9(nn.Module):
                 res[i]["context"] = context[i, :n].clone()
         return res
 
+    # Pocket-conditioned sampling (diffusion_qm9.py:362-371, :381-382).  The reference appends the pocket residues to
+    # the batch as extra nodes, but (a) its edge mask is BLOCK DIAGONAL - only the ligand-ligand and pocket-pocket blocks
+    # are set (:367-369), so no message or coordinate update ever crosses from pocket to ligand; (b) the pocket
+    # coordinates are frozen (en_dynamics.py:83-88) and the pocket rows are cut off eps (:325); (c) the only coupling
+    # left, the centre-of-gravity projection of en_dynamics.py:116 over ligand + pocket nodes, is undone by the second
+    # projection over the ligand alone (:330).  The ligand trajectory therefore does not depend on the pocket; the noise
+    # draws are ligand-shaped in both cases (:361, :337).  tests/golden/pocket_l1.npz records a reference run WITH a
+    # pocket and tests/test_oracle_golden.py / test_gpu_parity.py reproduce it with the ligand-only chain to ~1e-7 per
+    # step.  So the native path validates the pocket tensors and runs the ligand chain - same results, none of the
+    # pocket-pocket work.
+    RESIDUE_LIST = ["ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE",
+                    "PRO", "SER", "THR", "TRP", "TYR", "VAL"]
+
+    def _check_pocket_cond(self, pocket_cond, num_samples):
+        if not self.pocket:
+            raise ValueError("pocket_cond given but the model was built with cfg.pocket = False")
+        if len(pocket_cond) != 4:
+            raise ValueError("pocket_cond must be [residue_type, position, node_mask, edge_mask]")
+        feat, pos, nmask, emask = pocket_cond
+        P = feat.shape[1]
+        if (feat.shape != (num_samples, P) or tuple(pos.shape) != (num_samples, P, 3)
+                or tuple(nmask.shape) != (num_samples, P, 1) or tuple(emask.shape) != (num_samples, P, P)):
+            raise ValueError("pocket_cond shapes must be [B,P], [B,P,3], [B,P,1], [B,P,P]")
+        if int(feat.min()) < 0 or int(feat.max()) >= self.pocket_embed.num_embeddings:
+            raise IndexError("pocket residue type out of range")   # what nn.Embedding would raise in the reference
+
     def sample_batches(self, batch_size, num_batches, device, context_range=None, protein_data_all=None):
         """diffusion_qm9.py:397-436: ``(results, test_names)``."""
-        if protein_data_all is not None:
-            raise NotImplementedError("protein (pocket) conditioned sampling is not built yet")
+        cond_all = None
+        if protein_data_all is not None:   # :399-419: residue names -> indices (+1), padded pocket tensors
+            feats = [torch.tensor([self.RESIDUE_LIST.index(r) + 1 for r in d["residue_type"]]) for d in protein_data_all]
+            poss = [torch.as_tensor(d["coord"], dtype=torch.float32).reshape(-1, 3) for d in protein_data_all]
+            P = max(f.shape[0] for f in feats)
+            n = len(feats)
+            feat_t = torch.zeros(n, P, dtype=torch.long)
+            pos_t = torch.zeros(n, P, 3)
+            nmask = torch.zeros(n, P, 1, dtype=torch.bool)
+            emask = torch.zeros(n, P, P, dtype=torch.bool)
+            for i, (f, x) in enumerate(zip(feats, poss)):
+                k = f.shape[0]
+                feat_t[i, :k], pos_t[i, :k], nmask[i, :k, 0] = f, x, True
+                emask[i, :k, :k] = ~torch.eye(k, dtype=torch.bool)
+            cond_all = [feat_t, pos_t, nmask, emask]
         results, test_names = [], []
         for i in range(num_batches):
-            ctx = None if context_range is None else context_range[i % len(context_range)]
-            results.extend(self.sample(batch_size, device, context=ctx))
+            if cond_all is not None:
+                n = len(cond_all[0])
+                lo, hi = (i * batch_size) % n, ((i + 1) * batch_size - 1) % n + 1   # the reference's slice (:426)
+                cond = [t[lo:hi] for t in cond_all]
+                results.extend(self.sample(batch_size, device, pocket_cond=cond))
+                # names exactly as the reference builds them (:427): its modulus is len(protein_cond_all), the
+                # 4-element LIST of pocket tensors, not the number of pockets
+                q = len(cond_all)
+                test_names.extend(protein_data_all[j]["pocket_name"] + "/" + protein_data_all[j]["ligand_name"]
+                                  for j in range((i * batch_size) % q, ((i + 1) * batch_size) % q))
+            else:
+                ctx = None if context_range is None else context_range[i % len(context_range)]
+                results.extend(self.sample(batch_size, device, context=ctx))
         return results, test_names

@@ -83,7 +83,7 @@ class FixedNodes(nn.Module):
         return list(self.sizes)
 
 
-def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned", context_node_nf=0):
+def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned", context_node_nf=0, pocket=False):
     _install_stubs()
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -95,6 +95,7 @@ def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned", con
     cfg = to_attr(yaml.safe_load(open(os.path.join(REF, "conf/model/ddpmgblur.yaml")))["cfg"])
     cfg.dynamics.n_layers = n_layers
     cfg.dynamics.context_node_nf = context_node_nf
+    cfg.pocket = pocket
     cfg.timesteps = timesteps
     cfg.noise_schedule = noise_schedule
     if noise_schedule != "learned":
@@ -278,6 +279,63 @@ def case_context(name="context_l1", n_layers=1, T=6, sizes=(6, 9, 2), seed=3, co
     print(name, "eps absmax", float(eps.abs().max()), "x absmax", float(np.abs(x).max()))
 
 
+def case_pocket(name="pocket_l1", n_layers=1, T=6, sizes=(6, 9, 2), P=5, seed=4):
+    """Pocket-conditioned sampling (diffusion_qm9.py:362-371, :381-382; en_dynamics.py:83-88): the reference appends the
+    pocket residues as extra nodes with a block-diagonal edge mask and frozen coordinates."""
+    model = make_reference(n_layers, T, pocket=True)
+    sizes = list(sizes)
+    model.nodes_dist = FixedNodes(sizes)
+    B, N = len(sizes), max(sizes)
+    g = torch.Generator().manual_seed(seed)
+    n_res = [P, P - 2, P - 1][:B]
+    res_type = torch.zeros(B, P, dtype=torch.long)
+    res_pos = torch.zeros(B, P, 3)
+    res_mask = torch.zeros(B, P, 1).bool()
+    res_edge = torch.zeros(B, P, P).bool()
+    for i, n in enumerate(n_res):
+        res_type[i, :n] = torch.randint(1, 21, (n,), generator=g)
+        res_pos[i, :n] = torch.randn(n, 3, generator=g) * 3
+        res_mask[i, :n] = True
+        res_edge[i, :n, :n] = ~torch.eye(n, dtype=torch.bool)
+    draws, gam, zs = [], [], []
+    real_randn = torch.randn
+
+    def rec_randn(*a, **k):
+        v = real_randn(*a, **k)
+        draws.append(v.clone().numpy())
+        return v
+
+    h = model.gamma.register_forward_hook(
+        lambda m, i, o: gam.append((i[0].detach().clone().numpy(), o.detach().clone().numpy())))
+    real_step = model.sample_p_zs_given_zt
+
+    def rec_step(*a, **k):
+        v = real_step(*a, **k)
+        zs.append(v[:, :N].clone().numpy())
+        return v
+
+    model.sample_p_zs_given_zt = rec_step
+    torch.manual_seed(seed)
+    torch.randn = rec_randn
+    try:
+        res = model.sample(B, torch.device("cpu"), pocket_cond=[res_type, res_pos, res_mask, res_edge])
+    finally:
+        torch.randn = real_randn
+    h.remove()
+    x = np.zeros((B, N, 3), np.float32)
+    hh = np.zeros((B, N, 8), np.float32)
+    for i, r in enumerate(res):
+        x[i, :sizes[i]] = r["x"].numpy()
+        hh[i, :sizes[i]] = r["h"].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), randn_x=np.stack(draws[0::2]), randn_h=np.stack(draws[1::2]),
+                        gamma_in=np.stack([g_[0][:, 0] for g_ in gam]), gamma_out=np.stack([g_[1][:, 0] for g_ in gam]),
+                        z_traj=np.stack(zs).astype(np.float32), x=x, h=hh, sizes=np.array(sizes, np.int32),
+                        res_type=res_type.numpy(), res_pos=res_pos.numpy(), res_mask=res_mask.numpy(),
+                        res_edge=res_edge.numpy(), T=np.int32(T), n_layers=np.int32(n_layers),
+                        weight_seed=np.int32(2022), sample_seed=np.int32(seed))
+    print(name, "x absmax", float(np.abs(x).max()), "draw shapes", draws[0].shape, draws[1].shape, len(draws))
+
+
 def case_gamma():
     model = make_reference(1, 1000)
     t = torch.linspace(0, 1, 41).view(-1, 1)
@@ -317,5 +375,6 @@ if __name__ == "__main__":
     case_sample("sample_ragged_l9", n_layers=9, T=20, sizes=[10, 6, 9], seed=1)
     case_sample("sample_poly_l1", n_layers=1, T=10, sizes=[4, 8], seed=2, noise_schedule="polynomial_2")
     case_context()
+    case_pocket()
     case_gamma()
     case_nodes_dist()

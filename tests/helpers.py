@@ -25,12 +25,12 @@ def histogram_file(tmp_dir):
 
 
 def make_model(tmp_dir, n_layers, timesteps=1000, noise_schedule="learned", device="cpu", engine="fp32", seed=2022,
-               context_node_nf=0):
+               context_node_nf=0, pocket=False):
     """hierdiff_b200.DiffusionQM9 with the golden fixtures' weights (tests/golden/weightgen.py)."""
     from hierdiff_b200 import DiffusionQM9
     from hierdiff_b200.config import default_model_cfg
     cfg = default_model_cfg(n_layers=n_layers, timesteps=timesteps, noise_schedule=noise_schedule,
-                            analyze=histogram_file(tmp_dir), context_node_nf=context_node_nf)
+                            analyze=histogram_file(tmp_dir), context_node_nf=context_node_nf, pocket=pocket)
     model = DiffusionQM9(cfg)
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     sd = {k: torch.from_numpy(v) for k, v in fill_state_dict(shapes, seed).items()}

@@ -153,3 +153,13 @@ def test_unsupported_options_raise(tmp_path):
     with pytest.raises(ValueError):                     # ... and refuses a call without its context
         dyn.forward_sizes(torch.zeros(1), torch.zeros(1, 2, 11).cuda() if torch.cuda.is_available()
                           else _cpu_guard(), torch.ones(1, dtype=torch.int32))
+
+
+def test_pocket_model_keeps_reference_state_dict(tmp_path):
+    """cfg.pocket adds pocket_embed (diffusion_qm9.py:55-56) and nothing else."""
+    plain = make_model(tmp_path, n_layers=1, timesteps=5)
+    pocket = make_model(tmp_path, n_layers=1, timesteps=5, pocket=True)
+    extra = set(pocket.state_dict()) - set(plain.state_dict())
+    assert extra == {"pocket_embed.weight"} and tuple(pocket.state_dict()["pocket_embed.weight"].shape) == (21, 8)
+    with pytest.raises(ValueError):
+        plain._check_pocket_cond([torch.zeros(1, 2, dtype=torch.long)] * 4, 1)

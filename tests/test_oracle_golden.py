@@ -149,3 +149,27 @@ def test_context_forward_matches_reference(golden_dir):
     ctx = np.full((B, N, 1), g["context"], np.float32)
     eps = O.dynamics_forward(cfg, w, g["z"], g["t"], g["sizes"], context=ctx)
     assert rel(eps, g["eps"]) < 1e-5
+
+
+def test_pocket_conditioned_chain_equals_ligand_only_chain(golden_dir):
+    """Pocket-conditioned sampling (diffusion_qm9.py:362-371,:381-382).  The reference appends the pocket residues as
+    extra nodes, but with a BLOCK-DIAGONAL edge mask (ligand-ligand and pocket-pocket blocks only, :367-369), frozen
+    pocket coordinates (en_dynamics.py:83-88) and a second centre-of-gravity projection over the ligand alone (:330), so
+    the ligand trajectory does not depend on the pocket.  Proof by fixture: the reference ran WITH a pocket, the oracle
+    runs the ligand alone on the same draws and reproduces every z_t and the final (x, h)."""
+    g = np.load(os.path.join(golden_dir, "pocket_l1.npz"))
+    T, sizes = int(g["T"]), g["sizes"]
+    cfg, w = weights_for(int(g["n_layers"]))
+    z = masked_cog_noise(g["randn_x"][0], g["randn_h"][0], sizes)
+    B = z.shape[0]
+    for k in range(T):
+        s = T - 1 - k
+        t = np.full(B, np.float32(s + 1) / np.float32(T), np.float32)
+        eps = O.dynamics_forward(cfg, w, z, t, sizes)
+        z = O.reverse_step(z, eps, g["randn_x"][k + 1], g["randn_h"][k + 1], sizes,
+                           O.step_scalars(g["gamma_out"][2 * k], g["gamma_out"][2 * k + 1]))
+        assert rel(z, g["z_traj"][k]) < 2e-5, k
+    eps0 = O.dynamics_forward(cfg, w, z, np.zeros(B, np.float32), sizes)
+    x, h = O.final_decode(z, eps0, g["randn_x"][T + 1], g["randn_h"][T + 1], sizes,
+                          O.final_scalars(g["gamma_out"][2 * T]))
+    assert rel(x, g["x"]) < 2e-5 and rel(h, g["h"]) < 2e-5
