@@ -349,3 +349,29 @@ def test_pocket_conditioned_sample_matches_reference_fixture(tmp_path):
              "ligand_name": "l%d" % i} for i in range(B)]
     out, names = model.sample_batches(B, 1, dev(), protein_data_all=data)
     assert len(out) == B and names == ["p0/l0", "p1/l1", "p2/l2"]
+
+
+def test_en_variational_diffusion_adapter(tmp_path):
+    """EnVariationalDiffusion.sample(n_samples, n_nodes, node_mask, edge_mask, context) (en_diffusion.py:634-667) is
+    the same chain as DiffusionQM9.sample with caller-supplied masks and the EDM result layout."""
+    from hierdiff_b200 import EnVariationalDiffusion
+    from hierdiff_b200.utils import masks_from_sizes
+    qm9 = make_model(tmp_path, 1, timesteps=10, device=dev(), engine="strict")
+    edm = EnVariationalDiffusion(qm9.dynamics, in_node_nf=8, n_dims=3, timesteps=10).to(dev())
+    edm.gamma.load_state_dict(qm9.gamma.state_dict())
+    edm.engine = "strict"
+    sizes = [6, 9, 2, 9]
+    nm, em = masks_from_sizes(sizes, 9, dev())
+    torch.manual_seed(5)
+    x, h = edm.sample(4, 9, nm, em, None)
+    torch.manual_seed(5)
+    xq, hq = qm9.sample_padded(sizes, dev())
+    assert x.shape == (4, 9, 3) and x.device.type == "cuda"
+    assert torch.allclose(x.cpu(), xq, rtol=0, atol=1e-6 * float(xq.abs().max()))
+    assert h["categorical"].shape == (4, 9, 7) and h["integer"].shape == (4, 9, 1)
+    want_cat = torch.nn.functional.one_hot(torch.argmax(hq[..., :7], dim=2), 7) * nm.cpu().long()
+    assert torch.equal(h["categorical"].cpu(), want_cat)
+    assert torch.equal(h["integer"].cpu(), torch.round(hq[..., 7:]).long() * nm.cpu().long())
+    zs = edm.sample_p_zs_given_zt(torch.full((4, 1), 0.4, device=dev()), torch.full((4, 1), 0.5, device=dev()),
+                                  qm9.sample_combined_position_feature_noise(4, 9, nm), nm, em, None)
+    assert zs.shape == (4, 9, 11) and torch.isfinite(zs).all()
