@@ -17,6 +17,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution barrier over the cluster WITHOUT the cluster-scope fence of cluster_sync() (no MEMBAR.ALL.GPU / CCTL.IVALL):
+// shared-memory visibility inside each CTA comes from the __syncthreads() in front, mbarrier initialisation is published
+// to the peer by fence.mbarrier_init.release.cluster
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

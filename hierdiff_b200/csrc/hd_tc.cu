@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       }
     }
   }
+  if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   pdl_wait();   // row_off, sizes, x, the A|B operands: written by earlier kernels of the chain
   for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
-  if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 
   // ---- teardown ----------------------------------------------------------------------------------
   ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();   // the peer may still arrive on our barriers
   if (warp == MMA_WARP) ptx::tmem_dealloc<CG>(tmem, 512);
 }
 

@@ -11,6 +11,8 @@ void count_launch() {}
 bool pdl_enabled() { return false; }
 int linear_tc(const FwdCtx&, const float*, int, int, const float*, int, int, const void*, const void*, int, int,
               const float*, float*, int, int, const float*, bool) { return 0; }
+int linear_tc_v2_and_preproject(const FwdCtx&, const float*, const float*, float*, const void*, const void*, const float*,
+                                const void*, const void*, const float*, float*, bool) { return 0; }
 }
 
 template <bool GCL, bool STRICT>
@@ -49,7 +51,7 @@ static void run(const char* name, hd::tc::Params p) {
 
 int main() {
   using namespace hd;
-  const int B = 64, N = 40, BN = B * N;
+  const int B = getenv("HD_B") ? atoi(getenv("HD_B")) : 64, N = 40, BN = B * N;
   std::vector<float> h(BN * 512);
   for (auto& v : h) v = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
   float *ab, *x, *vec, *out;
