@@ -163,3 +163,23 @@ def test_pocket_model_keeps_reference_state_dict(tmp_path):
     assert extra == {"pocket_embed.weight"} and tuple(pocket.state_dict()["pocket_embed.weight"].shape) == (21, 8)
     with pytest.raises(ValueError):
         plain._check_pocket_cond([torch.zeros(1, 2, dtype=torch.long)] * 4, 1)
+
+
+REF_CONF = "/root/reference/endiffusion/conf"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONF), reason="the reference checkout only exists in the build container")
+def test_reference_config_tree_loads_unchanged():
+    """conf/sample.yaml of the reference (defaults list -> model/ddpmgblur.yaml, sample/default.yaml, analyze/GEOM.yaml)
+    composes unchanged and its `_target_: train_module.diffusion_qm9.DiffusionQM9` resolves to the native mirror."""
+    from hierdiff_b200 import DiffusionQM9
+    from hierdiff_b200.config import instantiate, load_config
+    cfg = load_config(REF_CONF, "sample", ["sample.batch_size=4"])
+    assert cfg.model["_target_"] == "train_module.diffusion_qm9.DiffusionQM9"
+    assert cfg.sample.batch_size == 4 and cfg.sample.num_batches == 16
+    model = instantiate(cfg.model, cfg=cfg, _recursive_=False)
+    assert isinstance(model, DiffusionQM9) and model.T == 1000
+    egnn = model.dynamics.egnn
+    assert (egnn.n_layers, egnn.hidden_nf, egnn.inv_sublayers) == (6, 256, 2)      # ddpmgblur.yaml:21-37
+    assert sum(p.numel() for p in model.dynamics.parameters()) == 5935386 - sum(p.numel() for p in model.gamma.parameters())
+    assert len(model.nodes_dist.n_nodes) == 67                                     # conf/analyze/GEOM.yaml
