@@ -5,7 +5,7 @@
  * FFI of its own for this path - the path is PyTorch library calls behind a Python class
  * surface - so each entry point below names the reference Python function whose
  * arithmetic it replaces (paths relative to /root/reference/endiffusion).  The Python
- * mirror in hierdiff_b200/*.py binds these through ctypes (INTEGRATION.md shows the stub
+ * mirror in the hierdiff_b200 package binds these through ctypes (INTEGRATION.md shows the stub
  * a maintainer of the reference would add).
  *
  * Conventions

@@ -183,3 +183,18 @@ def test_reference_config_tree_loads_unchanged():
     assert (egnn.n_layers, egnn.hidden_nf, egnn.inv_sublayers) == (6, 256, 2)      # ddpmgblur.yaml:21-37
     assert sum(p.numel() for p in model.dynamics.parameters()) == 5935386 - sum(p.numel() for p in model.gamma.parameters())
     assert len(model.nodes_dist.n_nodes) == 67                                     # conf/analyze/GEOM.yaml
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/hierdiff_b200.h compiles as C99 and examples/c_host.c links against the library and runs (host-only
+    entry points: sizes and capability queries, no GPU needed)."""
+    import subprocess
+    from hierdiff_b200 import native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.dirname(native.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "c_host.c"), "-L", libdir, "-lhierdiff_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.check_output([exe], text=True)
+    assert "parameters 3956497 floats" in out and "strict=1" in out and "hidden_nf=128 ->" in out
