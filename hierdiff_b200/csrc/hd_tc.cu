@@ -27,7 +27,9 @@ namespace hd {
 
 namespace tc {
 
-// per-role cycle accounting for scripts/edge_timing.cu (compiled out of the library)
+// per-role cycle accounting for scripts/edge_timing.cu (compiled out of the library).  The same harness builds the
+// ablation variants -DHD_EXP_NO_PROD_SILU / NO_EPI_SILU / NO_LO / NO_PASS2 / NO_LDG (results: profiles/r1_notes.md);
+// none of these macros is ever defined for the library.
 #ifdef HD_PHASE_TIMING
 __device__ long long g_acc[2][3][16];   // [CTA 10 | CTA 11][role][slot]
 // accumulate in registers (a global read-modify-write per stamp would stall the warp ~350 cycles), flush once

@@ -8,6 +8,8 @@ host->device copy.  Here a step is a fixed sequence of native ke
 on the device through a step counter, so the same captured graph is replayed for every step; the
 status word (NaN guard, mask / centre-of-gravity invariants) is read once after the loop.
 """
+import os
+
 import torch
 
 from . import native
@@ -152,6 +154,9 @@ class SamplingLoop:
                     native.ptr(self.z), native.stream_ptr()), "hd_combine_noise")
             else:
                 self.z.copy_(z_T)
+            nvtx = os.environ.get("HD_NVTX") == "1"    # ranges for nsys / ncu --nvtx captures
+            if nvtx:
+                torch.cuda.nvtx.range_push(f"hierdiff.chain B={self.B} N={self.N} T={T}")
             done = 0
             if self.graph is not None:
                 while done + self.graph_steps <= T:
@@ -160,5 +165,10 @@ class SamplingLoop:
             while done < T:
                 self._step()
                 done += 1
+            if nvtx:
+                torch.cuda.nvtx.range_push("hierdiff.final_decode")
             self._final()
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_pop()
         return self.x_out, self.h_out, self.flags
