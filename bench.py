@@ -351,11 +351,19 @@ def edge_kernel_roofline(model, loop, engine, B, N, iters=20):
         traffic = sum(float(m[k]["value"]) * unit[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except (OSError, KeyError, ValueError, IndexError):
         pass
+    # the kernel's second ceiling: every edge-channel needs two SiLU evaluations = 4 MUFU ops (ex2 + rcp, twice) in the
+    # strict engine, 2 (tanh, twice) in the fast one, at 16 MUFU lanes / clk / SM
+    mufu = (4.0 if engine == "strict" else 2.0 if engine == "fast" else 0.0) * edges * HIDDEN
+    props = torch.cuda.get_device_properties(dev)
+    sfu_floor_ms = mufu / (16.0 * props.multi_processor_count * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6) * 1e3
     achieved = flops / (ms * 1e-3) / 1e12
     return {"kernel": "fused GCL edge kernel (block 0, gcl_0)", "bound": "tensor", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_name,
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "tensor_passes": {"strict": 3, "fast": 1, "fp32": 0}[engine],
+            "sfu": {"mufu_ops_per_launch": mufu, "floor_ms": sfu_floor_ms,
+                    "frac": (sfu_floor_ms / ms) if mufu else None,
+                    "note": "co-bound: SiLU on every edge-channel twice; 16 MUFU lanes/clk/SM at sm_max_mhz"},
             "hbm_GBps_algorithmic": hbm_bytes / (ms * 1e-3) / 1e9,
             "hbm_frac_of_measured": hbm_bytes / (ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
             "note": "SURVEY.md 8d: the fused edge kernel is tensor-pipe bound (AI ~ 32*n FLOP/B); the HBM figure is "
