@@ -77,6 +77,11 @@ class DiffusionQM9(nn.Module):
         # native-path state
         self.steps_per_graph = int(_get(cfg, "steps_per_graph", 8) or 8)
         self.use_cuda_graph = bool(_get(cfg, "use_cuda_graph", True))
+        # sample_batches: run the num_batches independent batches as few large chains instead of one after the other
+        # (SURVEY 8f-1).  Off by default: the merged chain draws its noise with a different tensor shape, so under a
+        # fixed seed the molecules differ from the sequential run (same distribution, same sizes, same order).
+        self.merge_batches = bool(_get(cfg, "merge_batches", False))
+        self.max_chain_molecules = int(_get(cfg, "max_chain_molecules", 255) or 255)
         self._loops = {}
         self._table = None
         self._table_key = None
@@ -326,6 +331,10 @@ class DiffusionQM9(nn.Module):
                 emask[i, :k, :k] = ~torch.eye(k, dtype=torch.bool)
             cond_all = [feat_t, pos_t, nmask, emask]
         results, test_names = [], []
+        if self.merge_batches:
+            return self._sample_batches_merged(batch_size, num_batches, device, context_range, protein_data_all,
+                                               cond_all)
+        results, test_names = [], []
         for i in range(num_batches):
             if cond_all is not None:
                 n = len(cond_all[0])
@@ -340,4 +349,42 @@ class DiffusionQM9(nn.Module):
             else:
                 ctx = None if context_range is None else context_range[i % len(context_range)]
                 results.extend(self.sample(batch_size, device, context=ctx))
+        return results, test_names
+
+    def _sample_batches_merged(self, batch_size, num_batches, device, context_range, protein_data_all, cond_all):
+        """``sample_batches`` with the batches pooled: sizes (and contexts, pocket checks, names) are drawn per batch
+        in the reference's order, then the pool is sorted by size, cut into chains of at most
+        ``max_chain_molecules`` and the results are put back in batch order.  Molecules are independent
+        (SURVEY 8e), so this is the same sampler; only the noise stream is consumed in a different shape."""
+        sizes, ctx_vals, test_names = [], [], []
+        for i in range(num_batches):
+            if cond_all is not None:
+                n = len(cond_all[0])
+                lo, hi = (i * batch_size) % n, ((i + 1) * batch_size - 1) % n + 1
+                self._check_pocket_cond([t[lo:hi] for t in cond_all], batch_size)
+                q = len(cond_all)
+                test_names.extend(protein_data_all[j]["pocket_name"] + "/" + protein_data_all[j]["ligand_name"]
+                                  for j in range((i * batch_size) % q, ((i + 1) * batch_size) % q))
+            sizes.extend(int(v) for v in self.nodes_dist.sample(batch_size))
+            if cond_all is None and context_range is not None:
+                c = torch.as_tensor(context_range[i % len(context_range)], dtype=torch.float32).cpu()
+                if c.dim() > 1:
+                    raise NotImplementedError("merge_batches takes a scalar or a [context_node_nf] vector per batch")
+                ctx_vals.extend([c.reshape(-1)] * batch_size)
+        order = sorted(range(len(sizes)), key=lambda k: sizes[k])       # stable: ties keep batch order
+        cap = max(1, min(self.max_chain_molecules, 255))
+        results = [None] * len(sizes)
+        for lo in range(0, len(order), cap):
+            idx = order[lo:lo + cap]
+            chain_n = [sizes[k] for k in idx]
+            ctx = None
+            if ctx_vals:
+                per_mol = torch.stack([ctx_vals[k] for k in idx])                      # [chain, 1 or C]
+                ctx = torch.zeros(len(idx), max(chain_n), 1) + per_mol[:, None, :]
+            x, h = self.sample_padded(chain_n, device, context=ctx)
+            for r, k in enumerate(idx):
+                n = sizes[k]
+                results[k] = {"x": x[r, :n].clone(), "h": h[r, :n].clone()}
+                if ctx is not None:
+                    results[k]["context"] = ctx[r, :n].clone()
         return results, test_names

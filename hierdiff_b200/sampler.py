@@ -35,6 +35,8 @@ def main(argv=None):
     ap.add_argument("--out", default="sample_results.pkl")
     ap.add_argument("--engine", default=None, choices=["fp32", "strict", "fast"])
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--merge-batches", action="store_true",
+                    help="pool the rank's batches into few large chains (model.merge_batches)")
     ap.add_argument("--random-init", action="store_true", help="skip the checkpoint (plumbing / benchmarking)")
     ap.add_argument("overrides", nargs="*")
     args = ap.parse_args(argv)
@@ -52,6 +54,8 @@ def main(argv=None):
     parallel.broadcast_parameters(model, ctx)
     if args.engine:
         model.engine = args.engine
+    if args.merge_batches:
+        model.merge_batches = True
     n_local = parallel.shard_count(cfg.sample.num_batches, ctx)
     results, names = model.sample_batches(batch_size=cfg.sample.batch_size, num_batches=n_local, device=ctx.device,
                                           context_range=None)

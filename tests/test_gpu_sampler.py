@@ -157,6 +157,23 @@ def test_sample_api_layout_and_determinism(tmp_path):
     assert torch.equal(blob[0][3]["h"], res[3]["h"])
 
 
+def test_merged_sample_batches(tmp_path):
+    """merge_batches: same sizes in the same order as the sequential run, finite molecules, deterministic, and a
+    chain cap below the pool size gives several chains."""
+    model = make_model(tmp_path, 1, timesteps=12, device=dev(), engine="strict")
+    torch.manual_seed(0)
+    seq, _ = model.sample_batches(batch_size=2, num_batches=5, device=dev())
+    model.merge_batches, model.max_chain_molecules = True, 4
+    torch.manual_seed(0)
+    mer, names = model.sample_batches(batch_size=2, num_batches=5, device=dev())
+    assert names == [] and [r["x"].shape for r in mer] == [r["x"].shape for r in seq]
+    assert all(torch.isfinite(r["x"]).all() and torch.isfinite(r["h"]).all() for r in mer)
+    assert all(abs(float(r["x"].mean(0).abs().max())) < 1e-3 * max(1.0, float(r["x"].abs().max())) for r in mer)
+    torch.manual_seed(0)
+    mer2, _ = model.sample_batches(batch_size=2, num_batches=5, device=dev())
+    assert all(torch.equal(a["x"], b["x"]) and torch.equal(a["h"], b["h"]) for a, b in zip(mer, mer2))
+
+
 def test_eager_step_api_matches_loop(tmp_path):
     """sample_p_zs_given_zt / sample_p_xh_given_z0 with the reference's argument lists reproduce the loop."""
     from hierdiff_b200.utils import masks_from_sizes

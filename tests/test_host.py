@@ -198,3 +198,32 @@ def test_header_is_plain_c_and_links(tmp_path):
                            "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.check_output([exe], text=True)
     assert "parameters 3956497 floats" in out and "strict=1" in out and "hidden_nf=128 ->" in out
+
+
+def test_merged_sample_batches_bookkeeping(tmp_path):
+    """merge_batches: the pooled chains see the sizes / contexts of the reference's per-batch draws
+    (diffusion_qm9.py:349,:431-432), sorted by size and cut at max_chain_molecules, and every molecule comes back in
+    its batch-order slot.  The chain itself is replaced by a recorder, so this runs without a GPU."""
+    model = make_model(tmp_path, 1, timesteps=4, context_node_nf=1)
+    model.merge_batches, model.max_chain_molecules = True, 5
+    chains = []
+
+    def fake_chain(sample_n, device, z_T=None, context=None):
+        chains.append(list(sample_n))
+        B, N = len(sample_n), max(sample_n)
+        assert context.shape == (B, N, 1)
+        x = torch.tensor(sample_n, dtype=torch.float32).view(B, 1, 1).expand(B, N, 3).clone()
+        h = context.expand(B, N, 1).repeat(1, 1, 8).clone()
+        return x, h
+
+    model.sample_padded = fake_chain
+    torch.manual_seed(11)
+    out, names = model.sample_batches(4, 3, "cuda", context_range=[0.5, -2.0])
+    torch.manual_seed(11)
+    want = [int(n) for _ in range(3) for n in model.nodes_dist.sample(4)]   # the reference's draws, batch by batch
+    assert names == [] and [r["x"].shape[0] for r in out] == want
+    assert [len(c) for c in chains] == [5, 5, 2] and sum(chains, []) == sorted(want)
+    for k, r in enumerate(out):
+        c = [0.5, -2.0][(k // 4) % 2]
+        assert torch.all(r["x"] == want[k]) and torch.all(r["h"] == c) and torch.all(r["context"] == c)
+        assert r["h"].shape == (want[k], 8) and r["context"].shape == (want[k], 1)
