@@ -535,8 +535,8 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
     return HD_E_INVALID;
   }
   int32_t* row_off = engine == HD_ENGINE_FP32 ? nullptr : reinterpret_cast<int32_t*>(c.ws + c.W.row_off);
-  if (row_off && B > 255) {
-    set_error("tensor-core engine supports at most 255 molecules per call (got %d)", B);
+  if (row_off && B > 4096) {
+    set_error("tensor-core engine supports at most 4096 molecules per call (got %d)", B);
     return HD_E_INVALID;
   }
   HD_CHECK_CUDA(launch_pdl(prep_embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, z, t, context, C, sizes, B, N, F,

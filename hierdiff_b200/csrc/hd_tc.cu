@@ -56,7 +56,8 @@ constexpr int W_KG = 2048;            // bytes between K-adjacent core matrices 
 constexpr int W_HALF = (H / 8) * W_KG;  // 64 KB: one 128-row half image (hi or lo)
 constexpr int PMETA_BUFS = 2;         // producer-side row metadata: tiles t, t+1
 constexpr int EMETA_BUFS = 4;         // epilogue-side row metadata / group table: tiles t-2 .. t+1
-constexpr int MAX_B = 255;            // molecules per launch (row_off table in shared memory)
+constexpr int MAX_B = 255;            // molecules whose row_off table is staged in shared memory (larger: read from L2)
+constexpr int MAX_MOL = 4096;         // molecules per launch
 constexpr int NPW = 8;                // producer warps
 constexpr int NEW = 8;                // epilogue warps
 constexpr int PROD_THREADS = 32 * NPW, EPI_THREADS = 32 * NEW;
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   }
   if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   pdl_wait();   // row_off, sizes, x, the A|B operands: written by earlier kernels of the chain
-  for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
+  const bool big_b = p.B > MAX_B;       // table does not fit the shared-memory slot: searched in global memory
+  if (!big_b) for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();
   ptx::tc_fence_after();
@@ -222,11 +224,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 
   // ---- this CTA's rows ---------------------------------------------------------------------------
   const int nCTA = gridDim.x;
-  const int total = s_row[p.B];
+  const int* row_tab = big_b ? p.row_off : s_row;
+  const int total = row_tab[p.B];
   const int rpc = (total + nCTA - 1) / nCTA;
   auto range_of = [&](int c, int& a, int& e) {
-    a = align_recv(s_row, p.sizes, p.B, min(c * rpc, total));
-    e = align_recv(s_row, p.sizes, p.B, min((c + 1) * rpc, total));
+    a = align_recv(row_tab, p.sizes, p.B, min(c * rpc, total));
+    e = align_recv(row_tab, p.sizes, p.B, min((c + 1) * rpc, total));
   };
   int row_begin, row_end;
   range_of(blockIdx.x, row_begin, row_end);
@@ -565,9 +568,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         m.recv = m.send = -1;    // row outside this CTA's range
         e.flags = 0;
         if (R < row_end) {
-          const int b = find_mol(s_row, p.B, R);
+          int b, first;
+          if (big_b) {
+            b = find_mol(p.row_off, p.B, R);
+            first = __ldg(p.row_off + b);
+          } else {
+            b = find_mol(s_row, p.B, R);
+            first = s_row[b];
+          }
           const int n = p.sizes[b], npad = (n + 7) & ~7;
-          const int local = R - s_row[b];
+          const int local = R - first;
           const int i = local / npad, j = local - i * npad;
           m.recv = b * p.N + i;
           m.send = m.recv;
@@ -726,8 +736,8 @@ static int launch_edge(const Params& p, cudaStream_t st) {
 bool tc_available() { return true; }
 
 static int ensure_plan(const FwdCtx& c) {
-  if (c.B > tc::MAX_B) {
-    set_error("tensor-core engine supports at most %d molecules per call (got %d)", tc::MAX_B, c.B);
+  if (c.B > tc::MAX_MOL) {
+    set_error("tensor-core engine supports at most %d molecules per call (got %d)", tc::MAX_MOL, c.B);
     return HD_E_INVALID;
   }
   if (!c.planned) {

@@ -81,7 +81,7 @@ class DiffusionQM9(nn.Module):
         # (SURVEY 8f-1).  Off by default: the merged chain draws its noise with a different tensor shape, so under a
         # fixed seed the molecules differ from the sequential run (same distribution, same sizes, same order).
         self.merge_batches = bool(_get(cfg, "merge_batches", False))
-        self.max_chain_molecules = int(_get(cfg, "max_chain_molecules", 255) or 255)
+        self.max_chain_molecules = int(_get(cfg, "max_chain_molecules", 512) or 512)
         self._loops = {}
         self._table = None
         self._table_key = None
@@ -372,10 +372,12 @@ class DiffusionQM9(nn.Module):
                     raise NotImplementedError("merge_batches takes a scalar or a [context_node_nf] vector per batch")
                 ctx_vals.extend([c.reshape(-1)] * batch_size)
         order = sorted(range(len(sizes)), key=lambda k: sizes[k])       # stable: ties keep batch order
-        cap = max(1, min(self.max_chain_molecules, 255))
+        cap = max(1, min(self.max_chain_molecules, 4096))
+        n_chains = -(-len(order) // cap)
+        per = -(-len(order) // n_chains)                                # equal-sized chains, none left tiny
         results = [None] * len(sizes)
-        for lo in range(0, len(order), cap):
-            idx = order[lo:lo + cap]
+        for lo in range(0, len(order), per):
+            idx = order[lo:lo + per]
             chain_n = [sizes[k] for k in idx]
             ctx = None
             if ctx_vals:

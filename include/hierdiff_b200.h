@@ -97,7 +97,8 @@ HD_API int64_t hd_workspace_bytes(const hd_config* cfg, int32_t B, int32_t N);
 
 /* EGNN_dynamics_QM9._forward (models/module/en_dynamics.py:49-122) for mode 'egnn_dynamics',
  * condition_time=True, context=None:  eps = [velocity | h] [B,N,3+F], F = in_node_nf-1.
- * t is [B] (one time per molecule).  ORs HD_FLAG_NAN into *flags when the NaN guard fires. */
+ * t is [B] (one time per molecule).  ORs HD_FLAG_NAN into *flags when the NaN guard fires.
+ * Shape limits of the tensor-core engines: 1 <= N <= 128, 1 <= B <= 4096 (HD_E_INVALID otherwise). */
 HD_API int32_t hd_dynamics_forward(const hd_config* cfg, const void* packed, const float* z, const float* t,
                             const int32_t* sizes, int32_t B, int32_t N, float* eps, void* workspace,
                             int32_t* flags, int32_t engine, hd_stream_t stream);

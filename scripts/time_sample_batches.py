@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--timesteps", type=int, default=1000)
     ap.add_argument("--engine", default="strict")
     ap.add_argument("--repeats", type=int, default=2)
+    ap.add_argument("--caps", default="", help="comma list of max_chain_molecules values to time in merged mode")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     import numpy as np
@@ -39,8 +40,11 @@ def main():
     model.engine = args.engine
     out = {"batch_size": args.batch_size, "num_batches": args.num_batches, "n_layers": args.n_layers,
            "timesteps": args.timesteps, "engine": args.engine}
-    for mode in ("sequential", "merged"):
-        model.merge_batches = mode == "merged"
+    modes = ["sequential", "merged"] + [f"merged@{c}" for c in args.caps.split(",") if c]
+    for mode in modes:
+        model.merge_batches = mode != "sequential"
+        if "@" in mode:
+            model.max_chain_molecules = int(mode.split("@")[1])
         best = None
         for rep in range(args.repeats + 1):       # rep 0 captures the graphs of every (B, N) the seed produces
             torch.manual_seed(0)

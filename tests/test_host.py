@@ -222,7 +222,7 @@ def test_merged_sample_batches_bookkeeping(tmp_path):
     torch.manual_seed(11)
     want = [int(n) for _ in range(3) for n in model.nodes_dist.sample(4)]   # the reference's draws, batch by batch
     assert names == [] and [r["x"].shape[0] for r in out] == want
-    assert [len(c) for c in chains] == [5, 5, 2] and sum(chains, []) == sorted(want)
+    assert [len(c) for c in chains] == [4, 4, 4] and sum(chains, []) == sorted(want)
     for k, r in enumerate(out):
         c = [0.5, -2.0][(k // 4) % 2]
         assert torch.all(r["x"] == want[k]) and torch.all(r["h"] == c) and torch.all(r["context"] == c)
