@@ -86,15 +86,32 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
                                                     const float* __restrict__ wT, const float* __restrict__ bias,
                                                     float* __restrict__ x, float* __restrict__ x0,
                                                     float* __restrict__ x2, float* __restrict__ h,
-                                                    int32_t* __restrict__ nanflag, int32_t* __restrict__ row_off) {
+                                                    int32_t* __restrict__ nanflag, int32_t* __restrict__ row_off,
+                                                    int32_t* __restrict__ node_off) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_in[64];
+  __shared__ int s_part[8];
   const int D = 3 + F, Fi = F + 1 + C;
   const int64_t r = blockIdx.x;
   const int tid = threadIdx.x, b = (int)(r / N), i = (int)(r % N);
   const bool real = i < sizes[b];
   const float mk = real ? 1.f : 0.f;
+  // ragged node rows (node_off != null): node (b,i) lives in row sum_{b' < b} n_b' + i of x / x0 / x2 / h, padded
+  // nodes have no row.  Every block sums the sizes ahead of its molecule itself; block 0 also publishes the prefix
+  // table for the kernels that follow.
+  int64_t o = r;
+  if (node_off) {
+    int part = 0;
+    for (int k = tid; k < b; k += 256) part += sizes[k];
+    part = warp_sum_int(part);
+    if ((tid & 31) == 0) s_part[tid >> 5] = part;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base += s_part[w];
+    o = base + i;
+  }
   if (r == 0 && tid < 32) {
     if (tid == 0) *nanflag = 0;
     if (row_off) {
@@ -105,20 +122,38 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
         const int n = bb < B ? sizes[bb] : 0;
         int v = n * ((n + 7) & ~7);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, v, o);
-          if (tid >= o) v += u;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, v, o2);
+          if (tid >= o2) v += u;
         }
         if (bb < B) row_off[bb + 1] = carry + v;
         carry += __shfl_sync(0xffffffffu, v, 31);
       }
     }
+    if (node_off) {
+      int carry = 0;
+      if (tid == 0) node_off[0] = 0;
+      for (int base = 0; base < B; base += 32) {
+        const int bb = base + tid;
+        int v = bb < B ? sizes[bb] : 0;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, v, o2);
+          if (tid >= o2) v += u;
+        }
+        if (bb < B) node_off[bb + 1] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
   }
+  const bool wr = real || !node_off;   // ragged: padded nodes own no row
   if (tid < 3) {
     const float v = z[r * D + tid] * mk;
-    x[r * 3 + tid] = v;
-    x0[r * 3 + tid] = v;
-    x2[r * 3 + tid] = 0.f;   // ping-pong buffer of the coordinate updates: padded rows stay 0
+    if (wr) {
+      x[o * 3 + tid] = v;
+      x0[o * 3 + tid] = v;
+      x2[o * 3 + tid] = 0.f;   // ping-pong buffer of the coordinate updates: padded rows stay 0
+    }
   } else if (tid < D) {
     s_in[tid - 3] = z[r * D + tid] * mk;
   } else if (tid == D) {
@@ -132,7 +167,7 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
     v = bias[tid];
     for (int f = 0; f < Fi; ++f) v = fmaf(s_in[f], wT[f * H + tid], v);
   }
-  h[r * H + tid] = v;
+  if (wr) h[o * H + tid] = v;
 }
 
 // out_k + vel_k in one launch (the sampling path): one CTA per node row
@@ -140,17 +175,19 @@ __global__ void __launch_bounds__(256) out_vel_k(const float* __restrict__ h, co
                                                  const float* __restrict__ bias, int Fi, int F,
                                                  const int32_t* __restrict__ sizes, int N,
                                                  const float* __restrict__ xf, const float* __restrict__ x0,
-                                                 float* __restrict__ eps_raw, int32_t* __restrict__ nanflag) {
+                                                 float* __restrict__ eps_raw, int32_t* __restrict__ nanflag,
+                                                 const int32_t* __restrict__ node_off) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_out[64];
   const int64_t r = blockIdx.x;
   const int tid = threadIdx.x, b = (int)(r / N), i = (int)(r % N), warp = tid >> 5, lane = tid & 31;
   const bool real = i < sizes[b];
+  const int64_t o = node_off ? (real ? node_off[b] + i : 0) : r;   // row of h / xf / x0 (ragged: real nodes only)
   for (int f = warp; f < Fi; f += 8) {
     float s = 0.f;
     if (real)
-      for (int c = lane; c < H; c += 32) s = fmaf(h[r * H + c], w[f * H + c], s);
+      for (int c = lane; c < H; c += 32) s = fmaf(h[o * H + c], w[f * H + c], s);
     s = warp_sum(s);
     if (lane == 0) s_out[f] = real ? s + bias[f] : 0.f;
   }
@@ -159,7 +196,7 @@ __global__ void __launch_bounds__(256) out_vel_k(const float* __restrict__ h, co
   if (tid < D) {
     float v;
     if (tid < 3) {
-      v = (xf[r * 3 + tid] - x0[r * 3 + tid]) * (real ? 1.f : 0.f);
+      v = real ? xf[o * 3 + tid] - x0[o * 3 + tid] : 0.f;
       if (isnan(v)) atomicOr(nanflag, 1);
     } else {
       v = s_out[tid - 3];
@@ -510,6 +547,8 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
                                 const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
                                 int32_t N, float* eps, void* workspace, int32_t* flags, int32_t engine,
                                 hd_stream_t stream) {
+  const bool ragged = (engine & HD_ENGINE_RAGGED_ROWS) != 0;
+  engine &= ~HD_ENGINE_RAGGED_ROWS;
   int rc = check_common(cfg, packed, sizes, B, N, engine);
   if (rc) return rc;
   if (!z || !t || !eps || !workspace) {
@@ -535,19 +574,24 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
     return HD_E_INVALID;
   }
   int32_t* row_off = engine == HD_ENGINE_FP32 ? nullptr : reinterpret_cast<int32_t*>(c.ws + c.W.row_off);
+  // HD_ENGINE_RAGGED_ROWS on a tensor-core engine: only real nodes own a row of h / x / agg, so the node GEMMs do not
+  // pay for padding (B*N rows are still allocated, and the grids still cover them: see lin::Params::ragged)
+  int32_t* node_off = row_off && ragged ? reinterpret_cast<int32_t*>(c.ws + c.W.node_off) : nullptr;
   if (row_off && B > 4096) {
     set_error("tensor-core engine supports at most 4096 molecules per call (got %d)", B);
     return HD_E_INVALID;
   }
   HD_CHECK_CUDA(launch_pdl(prep_embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, z, t, context, C, sizes, B, N, F,
-                          PF(L.emb_wT), PF(L.emb_b), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), WF(c.W.h), nanflag, row_off));
+                          PF(L.emb_wT), PF(L.emb_b), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), WF(c.W.h), nanflag, row_off,
+                          node_off));
   count_launch();
   c.planned = row_off != nullptr;
+  c.node_off = node_off;
   float *hf = nullptr, *xf = nullptr;
   if ((rc = run_blocks(c, engine, &hf, &xf))) return rc;
   HD_CHECK_CUDA(launch_pdl(out_vel_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)hf, PF(L.out_w),
                           PF(L.out_b), Fi, F, sizes, N, (const float*)xf, (const float*)WF(c.W.x0), WF(c.W.eps_raw),
-                          nanflag));
+                          nanflag, (const int32_t*)node_off));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(cog_k, dim3(B), dim3(128), sizeof(float) * N * D, c.stream, (const float*)WF(c.W.eps_raw),
                           sizes, N, F, (const int32_t*)nanflag, eps, flags));

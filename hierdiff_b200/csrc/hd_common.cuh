@@ -108,6 +108,7 @@ struct Workspace {
   int64_t hout;   // [BN][Fi]
   int64_t eps_raw;// [BN][3+F]
   int64_t nanflag;// [1] int32 per forward
+  int64_t node_off;// [B+1] int32: prefix of n_b (ragged node rows of the sampling path, tensor-core engines)
   int64_t row_off;// [B+1] int32: prefix of n_b * pad8(n_b) (edge rows per molecule, tensor-core engines)
   int64_t total_bytes;
 };
@@ -149,6 +150,11 @@ __device__ __forceinline__ float sigmoid_acc(float v) { return 1.0f / (1.0f + ex
 // SiLU as the reference evaluates it, v * sigmoid(v) (ATen: x / (1 + exp(-x)))
 __device__ __forceinline__ float silu_acc(float v) { return v / (1.0f + expf(-v)); }
 
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -166,6 +172,7 @@ struct FwdCtx {
   const int32_t* sizes;
   int B, N;
   cudaStream_t stream;
+  const int32_t* node_off = nullptr;   // ragged node rows: [B+1] prefix of n_b; row of node (b,i) = node_off[b] + i
   mutable bool planned = false;  // ws.row_off holds the edge-row prefix for `sizes`
   mutable bool ab_ready = false; // ws.ab already holds the next sub-layer's A|B operands (fused node launch)
   bool x_prezeroed = false;      // padded rows of ws.x / ws.x2 are already 0 (hd_dynamics_forward): the coordinate

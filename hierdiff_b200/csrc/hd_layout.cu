@@ -165,6 +165,7 @@ Workspace make_workspace(const hd_config& c, int B, int N) {
   W.eps_raw = put(BN * (3 + Fi) * 4);
   W.nanflag = put(256);
   W.row_off = put(((int64_t)B + 1) * 4);
+  W.node_off = put(((int64_t)B + 1) * 4);
   W.total_bytes = p;
   return W;
 }

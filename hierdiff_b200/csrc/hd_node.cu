@@ -74,6 +74,8 @@ struct Params {
   const float* resid;
   const int32_t* sizes;
   int N;
+  int B, ragged;          // ragged node rows (hd_api.cu): the first sum(sizes) rows are real, all of them unmasked;
+                          // the grid covers the padded worst case and row tiles beyond the count retire at once
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -98,7 +100,7 @@ struct Params2 {
   int tiles_a;
 };
 
-template <bool STRICT, int NT>
+template <bool STRICT, int NT, bool RAGGED = false>
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   using S = Smem<STRICT, NT>;
   const bool second = (int)blockIdx.y >= pp.tiles_a;
@@ -128,14 +130,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
     ptx::fence_mbar_init();
   }
   if (tid < NT) s_bias[tid] = p.bias ? p.bias[ct * NT + tid] : 0.f;
+  int* s_cnt = nullptr;
+  if constexpr (RAGGED) {   // `sizes` is an input of the forward (no kernel of the chain writes it): summed ahead
+    __shared__ int s_cnt_buf[NTHREADS / 32];
+    s_cnt = s_cnt_buf;
+    int part = 0;           // of the dependency wait, like the rest of the set-up
+    for (int k = tid; k < p.B; k += NTHREADS) part += __ldg(p.sizes + k);
+    part = warp_sum_int(part);
+    if (lane == 0) s_cnt[warp] = part;
+  }
   if (warp == NPROD) ptx::tmem_alloc<1>(sbase + S::OFF_TMEM, NT);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *s_tmem;
   HD_STAMP(1, tid == 0);
+  int live = p.rows;
+  if constexpr (RAGGED) {
+    live = 0;
+#pragma unroll
+    for (int w = 0; w < NTHREADS / 32; ++w) live += s_cnt[w];
+  }
 
-  if (warp < NPROD) {
+  if (row0 >= live) {
+    // no real row in this tile
+  } else if (warp < NPROD) {
     // =========================== producers ===========================
     // warp w converts rows [16w, 16w+16) of every K chunk; a warp-wide 16-byte load covers two full 256-byte row
     // segments (fully coalesced), lane -> (row parity, 4 consecutive k)
@@ -148,7 +167,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = row0 + 16 * warp + 2 * i + rpar;
-        v[i] = row < p.rows ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)row * ld + col))
+        v[i] = row < live ? __ldg(reinterpret_cast<const float4*>(base + (int64_t)row * ld + col))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
 #pragma unroll
       for (int q = 0; q < NPASS; ++q) {
         const int row = row0 + RPP * q + orow;
-        rr[q] = row < p.rows ? *reinterpret_cast<const float4*>(p.resid + (int64_t)row * p.ldy + ct * NT + oc4)
+        rr[q] = row < live ? *reinterpret_cast<const float4*>(p.resid + (int64_t)row * p.ldy + ct * NT + oc4)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
@@ -240,10 +259,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
 #pragma unroll
     for (int q = 0; q < NPASS; ++q) {
       const int row = row0 + RPP * q + orow;
-      if (row >= p.rows) continue;
+      if (row >= live) continue;
       float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + (RPP * q + orow) * OT_LD + oc4);
       if (p.mode == 2) {
-        if ((row % p.N) < p.sizes[row / p.N]) {
+        if (RAGGED ? row < live : (row % p.N) < p.sizes[row / p.N]) {
           o.x += rr[q].x; o.y += rr[q].y; o.z += rr[q].z; o.w += rr[q].w;
         } else {
           o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -306,11 +325,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   HD_STAMP(10, tid == 32 * NPROD);
 }
 
-template <bool STRICT, int NT>
+template <bool STRICT, int NT, bool RAGGED = false>
 static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, cudaStream_t st) {
+  if constexpr (!RAGGED) {
+    if (a.ragged) return launch2<STRICT, NT, true>(a, n_out_a, b, n_out_b, st);
+  }
   using S = Smem<STRICT, NT>;
   static bool configured = false;
-  auto kern = linear_tc_k<STRICT, NT>;
+  auto kern = linear_tc_k<STRICT, NT, RAGGED>;
   if (!configured) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
@@ -351,6 +373,8 @@ static lin::Params make_params(const FwdCtx& c, const float* X1, int ld1, int K1
   p.resid = resid ? resid : Y;
   p.sizes = c.sizes;
   p.N = c.N;
+  p.B = c.B;
+  p.ragged = c.node_off != nullptr;
   return p;
 }
 

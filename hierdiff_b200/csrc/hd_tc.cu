@@ -80,6 +80,7 @@ struct Params {
   const float* x0;     // [BN][3] EGNN-entry coordinates
   const int32_t* sizes;
   const int32_t* row_off;  // [B+1] prefix of n_b * pad8(n_b)
+  const int32_t* node_off; // [B+1] prefix of n_b when the node rows are ragged, else null (row of (b,i) = b*N + i)
   const void* w_hi;    // bf16 images [2][32][128][8]
   const void* w_lo;
   const float *b2, *wa, *ba, *wr, *wd;
@@ -149,7 +150,9 @@ __host__ __device__ constexpr float silu_kout() { return STRICT ? -0.69314718055
 template <bool STRICT>
 __host__ __device__ constexpr float silu_kacc() { return STRICT ? 1.0f : -1.4426950408889634f; }
 
-template <bool GCL, bool STRICT, int CG>
+// WIDE: the variant for batches whose row table does not fit the shared-memory slot (B > MAX_B) and / or whose node
+// rows are ragged (p.node_off); the default instantiation carries neither branch.
+template <bool GCL, bool STRICT, int CG, bool WIDE = false>
 __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   using S = Smem<STRICT, CG>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   }
   if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   pdl_wait();   // row_off, sizes, x, the A|B operands: written by earlier kernels of the chain
-  const bool big_b = p.B > MAX_B;       // table does not fit the shared-memory slot: searched in global memory
+  const bool big_b = WIDE && p.B > MAX_B;   // table does not fit the shared-memory slot: searched in global memory
   if (!big_b) for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();
@@ -579,10 +582,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           const int n = p.sizes[b], npad = (n + 7) & ~7;
           const int local = R - first;
           const int i = local / npad, j = local - i * npad;
-          m.recv = b * p.N + i;
+          const int node0 = (WIDE && p.node_off) ? p.node_off[b] : b * p.N;
+          m.recv = node0 + i;
           m.send = m.recv;
           if (j < n) {
-            m.send = b * p.N + j;
+            m.send = node0 + j;
             e.flags = 1 | (j == i ? 2 : 0);
             const float* xi = p.x + 3 * (int64_t)m.recv;
             const float* xj = p.x + 3 * (int64_t)m.send;
@@ -701,11 +705,11 @@ static int sm_count() {
   return n;
 }
 
-template <bool GCL, bool STRICT, int CG>
+template <bool GCL, bool STRICT, int CG, bool WIDE = false>
 static int launch_edge(const Params& p, cudaStream_t st) {
   using S = Smem<STRICT, CG>;
   static bool configured = false;
-  auto kern = edge_tc_k<GCL, STRICT, CG>;
+  auto kern = edge_tc_k<GCL, STRICT, CG, WIDE>;
   if (!configured) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
@@ -762,6 +766,7 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   p.x0 = x0;
   p.sizes = c.sizes;
   p.row_off = reinterpret_cast<const int32_t*>(c.ws + c.W.row_off);
+  p.node_off = c.node_off;
   p.w_hi = c.packed + S.w2_hi;
   p.w_lo = c.packed + S.w2_lo;
   p.b2 = F(S.b2s);   // the -log2(e)-scaled copies (silu_scaled)
@@ -778,11 +783,16 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   p.norm_constant = c.cfg->norm_constant;
   p.norm_div = c.cfg->aggregation_mean ? (float)c.N : c.cfg->normalization_factor;
   const bool strict = engine == HD_ENGINE_TC_STRICT;
+  const bool wide = c.B > tc::MAX_B || c.node_off != nullptr;
   if (S.is_gcl) {
+    if (wide)
+      return strict ? tc::launch_edge<true, true, 2, true>(p, c.stream) : tc::launch_edge<true, false, 2, true>(p, c.stream);
     return strict ? tc::launch_edge<true, true, 2>(p, c.stream) : tc::launch_edge<true, false, 2>(p, c.stream);
   }
   if (!c.x_prezeroed)   // padded rows: x*mask = 0 (the kernel only writes the rows of real receivers)
     HD_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 3 * c.B * c.N, c.stream));
+  if (wide)
+    return strict ? tc::launch_edge<false, true, 2, true>(p, c.stream) : tc::launch_edge<false, false, 2, true>(p, c.stream);
   return strict ? tc::launch_edge<false, true, 2>(p, c.stream) : tc::launch_edge<false, false, 2>(p, c.stream);
 }
 

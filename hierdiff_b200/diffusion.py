@@ -81,7 +81,7 @@ class DiffusionQM9(nn.Module):
         # (SURVEY 8f-1).  Off by default: the merged chain draws its noise with a different tensor shape, so under a
         # fixed seed the molecules differ from the sequential run (same distribution, same sizes, same order).
         self.merge_batches = bool(_get(cfg, "merge_batches", False))
-        self.max_chain_molecules = int(_get(cfg, "max_chain_molecules", 512) or 512)
+        self.max_chain_molecules = int(_get(cfg, "max_chain_molecules", 1024) or 1024)
         self._loops = {}
         self._table = None
         self._table_key = None

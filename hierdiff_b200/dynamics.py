@@ -49,9 +49,10 @@ class EGNN_dynamics_QM9(nn.Module):
     def unwrap_forward(self):
         return self._forward
 
-    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None, context=None):
+    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None, context=None, ragged=False):
         """``_forward`` with the masks already reduced to ``sizes`` [B] int32 (no validation, no sync).
-        ``context`` [B,N,context_node_nf] is appended, unmasked, after the time channel (en_dynamics.py:76-79)."""
+        ``context`` [B,N,context_node_nf] is appended, unmasked, after the time channel (en_dynamics.py:76-79).
+        ``ragged``: performance hint (HD_ENGINE_RAGGED_ROWS) for batches with much padding; same results."""
         native.require_cuda(xh)
         B, N, D = xh.shape
         assert D == self.n_dims + self.in_node_nf - 1, (D, self.in_node_nf)
@@ -71,7 +72,8 @@ class EGNN_dynamics_QM9(nn.Module):
             native.check(native.lib().hd_dynamics_forward_ctx(
                 egnn.hd_config(), native.ptr(egnn.packed_weights()), native.ptr(xh), native.ptr(t),
                 native.ptr(context), C, native.ptr(sizes), B, N, native.ptr(eps),
-                native.ptr(egnn.workspace(B, N, xh.device)), native.ptr(flags), egnn.engine_id(engine),
+                native.ptr(egnn.workspace(B, N, xh.device)), native.ptr(flags),
+                egnn.engine_id(engine) | (native.ENGINE_RAGGED_ROWS if ragged else 0),
                 native.stream_ptr()), "hd_dynamics_forward_ctx")
         return eps
 

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libhierdiff_b200.so")
 ENGINE_FP32 = 0
 ENGINE_TC_STRICT = 1
 ENGINE_TC_FAST = 2
+ENGINE_RAGGED_ROWS = 0x100   # hint bit for hd_dynamics_forward[_ctx]: sum(sizes) << B*N
 ENGINES = {"fp32": ENGINE_FP32, "strict": ENGINE_TC_STRICT, "fast": ENGINE_TC_FAST}
 
 FLAG_NAN = 1

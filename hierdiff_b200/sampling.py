@@ -70,9 +70,20 @@ class SamplingLoop:
         self.table = None
         self.use_graph = use_graph
         self.steps_per_graph = steps_per_graph
-        self.graph = None
+        self.ragged = False        # HD_ENGINE_RAGGED_ROWS hint of the current sizes (see ragged_rows_pay)
+        self._graphs = {}          # hint -> captured graph (the hint is baked into the captured launches)
         self.graph_steps = 0
         self.launches_per_step = None
+
+    @property
+    def graph(self):
+        return self._graphs.get(self.ragged)
+
+    @staticmethod
+    def ragged_rows_pay(sizes_host, B, N):
+        """Compacting the node rows pays once the padded rows B*N no longer fit one wave of node-GEMM CTAs
+        (~3000 rows) and a good part of them is padding; below that it only adds set-up work."""
+        return B * N >= 3072 and int(sum(int(v) for v in sizes_host)) <= 0.75 * B * N
 
     # -- one reverse step, everything enqueued on the current stream --------------------------------
     def _step(self):
@@ -80,7 +91,8 @@ class SamplingLoop:
         st = native.stream_ptr()
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
                                      self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
-        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context)
+        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
+                                 ragged=self.ragged)
         self.rx.normal_()
         self.rh.normal_()
         native.check(L.hd_reverse_step(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
@@ -93,7 +105,8 @@ class SamplingLoop:
         st = native.stream_ptr()
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
                                      self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
-        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context)
+        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
+                                 ragged=self.ragged)
         self.rx.normal_()
         self.rh.normal_()
         nv, nb = m.norm_values, m.norm_biases
@@ -121,7 +134,7 @@ class SamplingLoop:
         self.flags.copy_(saved[2])
         torch.cuda.synchronize(self.device)
         torch.cuda.set_rng_state(rng, self.device)
-        self.graph, self.graph_steps = g, k
+        self._graphs[self.ragged], self.graph_steps = g, k
 
     def prepare(self, table):
         """Bind the schedule table and (re)capture the graph; not part of a sample's timed region."""
@@ -138,6 +151,9 @@ class SamplingLoop:
         T = self.table.T
         if (context is None) != (self.context is None):
             raise ValueError("context must be given exactly when the dynamics has context_node_nf > 0")
+        sizes_list = sizes_host.tolist() if hasattr(sizes_host, "tolist") else list(sizes_host)
+        self.ragged = self.ragged_rows_pay(sizes_list, self.B, self.N)
+        self.prepare(self.table)        # first chain with this hint: capture its graph
         with torch.cuda.device(self.device):
             self.sizes.copy_(torch.as_tensor(sizes_host, dtype=torch.int32), non_blocking=True)
             if context is not None:

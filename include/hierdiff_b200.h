@@ -46,6 +46,10 @@ extern "C" {
 #define HD_ENGINE_FP32 0      /* CUDA-core fp32 FFMA kernels (reference-order arithmetic)          */
 #define HD_ENGINE_TC_STRICT 1 /* tcgen05 tensor cores, bf16x3 split operands, fp32 accumulate      */
 #define HD_ENGINE_TC_FAST 2   /* tcgen05 tensor cores, single bf16 operands, fast SiLU             */
+/* May be OR-ed into the `engine` argument of hd_dynamics_forward[_ctx]: a performance hint that sum(sizes) is well
+ * below B*N.  The tensor-core engines then keep one workspace row per REAL node (instead of B*N rows), so the
+ * per-node GEMMs skip the padding.  Results are bit-identical with and without the hint. */
+#define HD_ENGINE_RAGGED_ROWS 0x100
 
 /* bits of the device-side status word (`flags`) that kernels OR into */
 #define HD_FLAG_NAN 1       /* en_dynamics.py:109-111 NaN guard fired (velocity zeroed)            */

@@ -27,8 +27,8 @@ def model4(tmp_path_factory):
     return make_model(tmp_path_factory.mktemp("m4"), 4, device=dev())
 
 
-def fwd(model, z, t, sizes):
-    eps = model.dynamics.forward_sizes(cuda(t), cuda(z), cuda(sizes, torch.int32))
+def fwd(model, z, t, sizes, ragged=False):
+    eps = model.dynamics.forward_sizes(cuda(t), cuda(z), cuda(sizes, torch.int32), ragged=ragged)
     torch.cuda.synchronize()
     return eps.cpu().numpy()
 
@@ -244,6 +244,45 @@ def test_extreme_shapes(model4, B, N):
     got = fwd(model4, z, t, sizes)
     assert np.isfinite(got).all()
     assert rel(got, ref) < 5e-5
+
+
+@pytest.mark.parametrize("engine", ["strict", "fast"])
+@pytest.mark.parametrize("B,N", [(5, 9), (64, 40), (60, 83), (700, 12)])
+def test_ragged_row_hint_is_bit_identical(model4, engine, B, N):
+    """HD_ENGINE_RAGGED_ROWS (one workspace row per real node, dead node-GEMM tiles retire at once) changes where the
+    rows live, not what is computed: same bits as the padded layout, for sizes from 1 to N and for full batches."""
+    rng = np.random.default_rng(B + N)
+    use(model4, engine)
+    for full in (False, True):
+        sizes = np.full(B, N, np.int32) if full else rng.integers(1, N + 1, B).astype(np.int32)
+        z, t = random_batch(B, N, sizes, seed=B)
+        a = fwd(model4, z, t, sizes)
+        b = fwd(model4, z, t, sizes, ragged=True)
+        assert np.isfinite(a).all() and np.array_equal(a, b)
+    sizes = np.ones(B, np.int32)                       # single-node molecules: no edge at all
+    z, t = random_batch(B, N, sizes, seed=1)
+    assert np.array_equal(fwd(model4, z, t, sizes), fwd(model4, z, t, sizes, ragged=True))
+
+
+def test_ragged_hint_is_chosen_per_chain(tmp_path):
+    """SamplingLoop picks the hint from the host-side sizes and keeps one captured graph per hint; the chain's
+    result does not depend on it."""
+    model = make_model(tmp_path, 1, timesteps=16, device=dev(), engine="strict")
+    B, N = 80, 40
+    loop = model.sampling_loop(B, N, dev())
+    small = [3] * (B - 1) + [N]
+    assert loop.ragged_rows_pay(small, B, N) and not loop.ragged_rows_pay([N] * B, B, N)
+    assert not loop.ragged_rows_pay([3] * 7 + [N], 8, N)
+    torch.manual_seed(1)
+    xa, ha = model.sample_padded(small, dev())
+    assert loop.ragged and loop.graph is not None
+    torch.manual_seed(1)
+    xf, _ = model.sample_padded([N] * B, dev())
+    assert not loop.ragged and len(loop._graphs) == 2
+    loop.ragged_rows_pay = lambda *a: False             # same chain, padded rows
+    torch.manual_seed(1)
+    xb, hb = model.sample_padded(small, dev())
+    assert not loop.ragged and torch.equal(xa, xb) and torch.equal(ha, hb)
 
 
 def test_too_many_molecules_is_an_error_not_a_fallback(model4):
