@@ -1,5 +1,5 @@
 // Phase timing of the node GEMM kernel (one CTA's globaltimer stamps) at the C2 shape.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DHD_PHASE_TIMING -o gpurun_out/node_timing scripts/node_timing.cu hierdiff_b200/csrc/hd_layout.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DHD_PHASE_TIMING -o gpurun_out/node_timing scripts/node_timing.cu
 #include <cstdio>
 #include <vector>
 #include "../hierdiff_b200/csrc/hd_node.cu"
