@@ -11,4 +11,15 @@ with tempfile.TemporaryDirectory() as tmp:
             model.engine=eng
             eps=model.dynamics.forward_sizes(torch.from_numpy(t).to(dev),torch.from_numpy(z).to(dev),torch.tensor(sizes,dtype=torch.int32,device=dev))
             torch.cuda.synchronize(); print(eng,sizes,float(eps.abs().max()))
+    # ragged node rows and the >255-molecule row table (edge_tc_k<..., WIDE>, linear_tc_k<..., RAGGED>)
+    rng=np.random.default_rng(0)
+    for B,N in ((9,20),(300,6)):
+        sizes=rng.integers(1,N+1,B).astype(np.int32); sizes[0]=N
+        z,t=random_batch(B,N,sizes,seed=2)
+        for eng in ('strict','fast'):
+            model.engine=eng
+            for ragged in (False,True):
+                eps=model.dynamics.forward_sizes(torch.from_numpy(t).to(dev),torch.from_numpy(z).to(dev),torch.from_numpy(sizes).to(dev),ragged=ragged)
+                torch.cuda.synchronize(); print(eng,B,N,'ragged' if ragged else 'padded',float(eps.abs().max()))
+    model.engine='strict'
     torch.manual_seed(0); print(len(model.sample(3,dev)))
