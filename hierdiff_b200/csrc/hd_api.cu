@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
                                                     float* __restrict__ x, float* __restrict__ x0,
                                                     float* __restrict__ x2, float* __restrict__ h,
                                                     int32_t* __restrict__ nanflag, int32_t* __restrict__ row_off,
-                                                    int32_t* __restrict__ node_off) {
+                                                    int32_t* __restrict__ node_off, int rows_bound,
+                                                    int32_t* __restrict__ flags) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_in[64];
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
   // table for the kernels that follow.
   int64_t o = r;
   if (node_off) {
+    if (!real && r != 0) return;   // a padded node owns no row (block 0 stays: it publishes the prefix tables)
     int part = 0;
     for (int k = tid; k < b; k += 256) part += sizes[k];
     part = warp_sum_int(part);
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
         if (bb < B) node_off[bb + 1] = carry + v;
         carry += __shfl_sync(0xffffffffu, v, 31);
       }
+      // the caller's bound on sum(sizes) sized the node-GEMM grids: rows beyond it would silently go missing
+      if (tid == 0 && carry > rows_bound && flags) atomicOr(flags, HD_FLAG_MASK);
     }
   }
   const bool wr = real || !node_off;   // ragged: padded nodes own no row
@@ -547,6 +551,19 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
                                 const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
                                 int32_t N, float* eps, void* workspace, int32_t* flags, int32_t engine,
                                 hd_stream_t stream) {
+  return hd_dynamics_forward_ragged(cfg, packed, z, t, context, context_nf, sizes, B, N, 0, eps, workspace, flags,
+                                    engine, stream);
+}
+
+HD_API int32_t hd_dynamics_forward_ragged(const hd_config* cfg, const void* packed, const float* z, const float* t,
+                                   const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
+                                   int32_t N, int32_t live_rows, float* eps, void* workspace, int32_t* flags,
+                                   int32_t engine, hd_stream_t stream) {
+  if (live_rows < 0 || (int64_t)live_rows > (int64_t)B * N) {
+    set_error("live_rows=%d outside [0, B*N]", live_rows);
+    return HD_E_INVALID;
+  }
+  if (live_rows > 0) engine |= HD_ENGINE_RAGGED_ROWS;
   const bool ragged = (engine & HD_ENGINE_RAGGED_ROWS) != 0;
   engine &= ~HD_ENGINE_RAGGED_ROWS;
   int rc = check_common(cfg, packed, sizes, B, N, engine);
@@ -583,10 +600,11 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
   }
   HD_CHECK_CUDA(launch_pdl(prep_embed_k, dim3((unsigned)BN), dim3(256), 0, c.stream, z, t, context, C, sizes, B, N, F,
                           PF(L.emb_wT), PF(L.emb_b), WF(c.W.x), WF(c.W.x0), WF(c.W.x2), WF(c.W.h), nanflag, row_off,
-                          node_off));
+                          node_off, live_rows > 0 ? live_rows : (int)BN, flags));
   count_launch();
   c.planned = row_off != nullptr;
   c.node_off = node_off;
+  c.rows_bound = node_off && live_rows > 0 ? live_rows : 0;
   float *hf = nullptr, *xf = nullptr;
   if ((rc = run_blocks(c, engine, &hf, &xf))) return rc;
   HD_CHECK_CUDA(launch_pdl(out_vel_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)hf, PF(L.out_w),

@@ -173,6 +173,7 @@ struct FwdCtx {
   int B, N;
   cudaStream_t stream;
   const int32_t* node_off = nullptr;   // ragged node rows: [B+1] prefix of n_b; row of node (b,i) = node_off[b] + i
+  int rows_bound = 0;                  // ragged node rows: the caller's bound on sum(sizes) (0: B*N); sizes the node-GEMM grids
   mutable bool planned = false;  // ws.row_off holds the edge-row prefix for `sizes`
   mutable bool ab_ready = false; // ws.ab already holds the next sub-layer's A|B operands (fused node launch)
   bool x_prezeroed = false;      // padded rows of ws.x / ws.x2 are already 0 (hd_dynamics_forward): the coordinate

@@ -69,6 +69,7 @@ struct Params {
   const void* w_lo;
   const float* bias;      // [n_out] or null
   float* Y;
+  int grid_rows;          // rows the launch covers (<= rows: the caller's bound on the real rows when ragged)
   int ldy, rows, mode;    // mode 0: store, 1: SiLU, 2: (resid + v) * node_mask, 3: store K-chunk-major
                           // Y[col/16][row][col%16] (the edge kernel's A|B operand layout)
   const float* resid;
@@ -341,7 +342,7 @@ static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, c
   pp.a = a;
   pp.b = b ? *b : a;
   pp.tiles_a = n_out_a / NT;
-  dim3 grid((a.rows + TM - 1) / TM, pp.tiles_a + (b ? n_out_b / NT : 0));
+  dim3 grid((a.grid_rows + TM - 1) / TM, pp.tiles_a + (b ? n_out_b / NT : 0));
   HD_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), S::TOTAL, st, pp));
   count_launch();
   return HD_OK;
@@ -369,6 +370,7 @@ static lin::Params make_params(const FwdCtx& c, const float* X1, int ld1, int K1
   p.Y = Y;
   p.ldy = ldy;
   p.rows = c.B * c.N;
+  p.grid_rows = c.node_off && c.rows_bound > 0 ? c.rows_bound : p.rows;
   p.mode = mode;
   p.resid = resid ? resid : Y;
   p.sizes = c.sizes;

@@ -49,10 +49,12 @@ class EGNN_dynamics_QM9(nn.Module):
     def unwrap_forward(self):
         return self._forward
 
-    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None, context=None, ragged=False):
+    def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None, context=None, ragged=False,
+                      live_rows=0):
         """``_forward`` with the masks already reduced to ``sizes`` [B] int32 (no validation, no sync).
         ``context`` [B,N,context_node_nf] is appended, unmasked, after the time channel (en_dynamics.py:76-79).
-        ``ragged``: performance hint (HD_ENGINE_RAGGED_ROWS) for batches with much padding; same results."""
+        ``ragged``: performance hint (HD_ENGINE_RAGGED_ROWS) for batches with much padding; same results.
+        ``live_rows``: with ``ragged``, a host-side bound >= sum(sizes) that sizes the node-GEMM grids (0: B*N)."""
         native.require_cuda(xh)
         B, N, D = xh.shape
         assert D == self.n_dims + self.in_node_nf - 1, (D, self.in_node_nf)
@@ -69,12 +71,12 @@ class EGNN_dynamics_QM9(nn.Module):
         eps = torch.empty_like(xh) if out is None else out
         egnn = self.egnn
         with torch.cuda.device(xh.device):
-            native.check(native.lib().hd_dynamics_forward_ctx(
+            native.check(native.lib().hd_dynamics_forward_ragged(
                 egnn.hd_config(), native.ptr(egnn.packed_weights()), native.ptr(xh), native.ptr(t),
-                native.ptr(context), C, native.ptr(sizes), B, N, native.ptr(eps),
+                native.ptr(context), C, native.ptr(sizes), B, N, int(live_rows) if ragged else 0, native.ptr(eps),
                 native.ptr(egnn.workspace(B, N, xh.device)), native.ptr(flags),
                 egnn.engine_id(engine) | (native.ENGINE_RAGGED_ROWS if ragged else 0),
-                native.stream_ptr()), "hd_dynamics_forward_ctx")
+                native.stream_ptr()), "hd_dynamics_forward_ragged")
         return eps
 
     def _forward(self, t, xh, node_mask, edge_mask, context, mol_shape=None):

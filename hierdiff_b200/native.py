@@ -19,7 +19,7 @@ FLAG_NAN = 1
 FLAG_COG = 2
 FLAG_MASK = 4
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class HdConfig(ctypes.Structure):
@@ -53,6 +53,7 @@ SIGNATURES = {
     "hd_workspace_bytes": (ctypes.c_int64, [_CFG, _I, _I]),
     "hd_dynamics_forward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P]),
     "hd_dynamics_forward_ctx": (_I, [_CFG, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P]),
+    "hd_dynamics_forward_ragged": (_I, [_CFG, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "hd_egnn_forward": (_I, [_CFG, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P]),
     "hd_gcl_forward": (_I, [_CFG, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
     "hd_equiv_update": (_I, [_CFG, _P, _I, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),

@@ -71,13 +71,14 @@ class SamplingLoop:
         self.use_graph = use_graph
         self.steps_per_graph = steps_per_graph
         self.ragged = False        # HD_ENGINE_RAGGED_ROWS hint of the current sizes (see ragged_rows_pay)
-        self._graphs = {}          # hint -> captured graph (the hint is baked into the captured launches)
+        self.live_rows = 0         # with the hint: sum(sizes) rounded up to whole 128-row tiles (sizes the node grids)
+        self._graphs = {}          # (hint, live_rows) -> captured graph (both are baked into the captured launches)
         self.graph_steps = 0
         self.launches_per_step = None
 
     @property
     def graph(self):
-        return self._graphs.get(self.ragged)
+        return self._graphs.get((self.ragged, self.live_rows))
 
     @staticmethod
     def ragged_rows_pay(sizes_host, B, N):
@@ -92,7 +93,7 @@ class SamplingLoop:
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
                                      self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
         m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
-                                 ragged=self.ragged)
+                                 ragged=self.ragged, live_rows=self.live_rows)
         self.rx.normal_()
         self.rh.normal_()
         native.check(L.hd_reverse_step(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
@@ -106,7 +107,7 @@ class SamplingLoop:
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
                                      self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
         m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
-                                 ragged=self.ragged)
+                                 ragged=self.ragged, live_rows=self.live_rows)
         self.rx.normal_()
         self.rh.normal_()
         nv, nb = m.norm_values, m.norm_biases
@@ -134,7 +135,7 @@ class SamplingLoop:
         self.flags.copy_(saved[2])
         torch.cuda.synchronize(self.device)
         torch.cuda.set_rng_state(rng, self.device)
-        self._graphs[self.ragged], self.graph_steps = g, k
+        self._graphs[(self.ragged, self.live_rows)], self.graph_steps = g, k
 
     def prepare(self, table):
         """Bind the schedule table and (re)capture the graph; not part of a sample's timed region."""
@@ -153,6 +154,7 @@ class SamplingLoop:
             raise ValueError("context must be given exactly when the dynamics has context_node_nf > 0")
         sizes_list = sizes_host.tolist() if hasattr(sizes_host, "tolist") else list(sizes_host)
         self.ragged = self.ragged_rows_pay(sizes_list, self.B, self.N)
+        self.live_rows = -(-int(sum(sizes_list)) // 128) * 128 if self.ragged else 0
         self.prepare(self.table)        # first chain with this hint: capture its graph
         with torch.cuda.device(self.device):
             self.sizes.copy_(torch.as_tensor(sizes_host, dtype=torch.int32), non_blocking=True)

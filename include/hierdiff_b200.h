@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 2
+#define HD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -114,6 +114,14 @@ HD_API int32_t hd_dynamics_forward_ctx(const hd_config* cfg, const void* packed,
                                 const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
                                 int32_t N, float* eps, void* workspace, int32_t* flags, int32_t engine,
                                 hd_stream_t stream);
+
+/* hd_dynamics_forward_ctx with ragged node rows (HD_ENGINE_RAGGED_ROWS) and a host-side bound: live_rows >=
+ * sum(sizes) (1..B*N; 0 = no bound, as _ctx).  The per-node GEMM grids are sized for live_rows instead of B*N, so a
+ * batch with much padding launches no dead CTAs at all.  A bound below sum(sizes) ORs HD_FLAG_MASK into *flags. */
+HD_API int32_t hd_dynamics_forward_ragged(const hd_config* cfg, const void* packed, const float* z, const float* t,
+                                   const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
+                                   int32_t N, int32_t live_rows, float* eps, void* workspace, int32_t* flags,
+                                   int32_t engine, hd_stream_t stream);
 
 /* EGNN.forward (models/layers/egnn_new.py:192-205) on the canonical dense edge list of
  * en_dynamics.py:124-143.  h_in [B*N,in_node_nf], x_in [B*N,3] -> h_out [B*N,in_node_nf], x_out. */

@@ -27,8 +27,8 @@ def model4(tmp_path_factory):
     return make_model(tmp_path_factory.mktemp("m4"), 4, device=dev())
 
 
-def fwd(model, z, t, sizes, ragged=False):
-    eps = model.dynamics.forward_sizes(cuda(t), cuda(z), cuda(sizes, torch.int32), ragged=ragged)
+def fwd(model, z, t, sizes, ragged=False, live_rows=0):
+    eps = model.dynamics.forward_sizes(cuda(t), cuda(z), cuda(sizes, torch.int32), ragged=ragged, live_rows=live_rows)
     torch.cuda.synchronize()
     return eps.cpu().numpy()
 
@@ -258,10 +258,24 @@ def test_ragged_row_hint_is_bit_identical(model4, engine, B, N):
         z, t = random_batch(B, N, sizes, seed=B)
         a = fwd(model4, z, t, sizes)
         b = fwd(model4, z, t, sizes, ragged=True)
-        assert np.isfinite(a).all() and np.array_equal(a, b)
+        c = fwd(model4, z, t, sizes, ragged=True, live_rows=int(sizes.sum()))     # grids sized by the host's bound
+        assert np.isfinite(a).all() and np.array_equal(a, b) and np.array_equal(a, c)
     sizes = np.ones(B, np.int32)                       # single-node molecules: no edge at all
     z, t = random_batch(B, N, sizes, seed=1)
     assert np.array_equal(fwd(model4, z, t, sizes), fwd(model4, z, t, sizes, ragged=True))
+
+
+def test_ragged_bound_below_the_real_rows_is_flagged(model4):
+    from hierdiff_b200 import native
+    B, N = 6, 30
+    sizes = np.full(B, N, np.int32)
+    z, t = random_batch(B, N, sizes, seed=3)
+    use(model4, "strict")
+    for bound, want in ((B * N, 0), (B * N - 1, native.FLAG_MASK)):
+        flags = torch.zeros(1, dtype=torch.int32, device=dev())
+        model4.dynamics.forward_sizes(cuda(t), cuda(z), cuda(sizes, torch.int32), flags=flags, ragged=True,
+                                      live_rows=bound)
+        assert int(flags.item()) & native.FLAG_MASK == want
 
 
 def test_ragged_hint_is_chosen_per_chain(tmp_path):
@@ -275,10 +289,10 @@ def test_ragged_hint_is_chosen_per_chain(tmp_path):
     assert not loop.ragged_rows_pay([3] * 7 + [N], 8, N)
     torch.manual_seed(1)
     xa, ha = model.sample_padded(small, dev())
-    assert loop.ragged and loop.graph is not None
+    assert loop.ragged and loop.live_rows == 384 and loop.graph is not None     # 79*3 + 40 = 277 -> 3 tiles
     torch.manual_seed(1)
     xf, _ = model.sample_padded([N] * B, dev())
-    assert not loop.ragged and len(loop._graphs) == 2
+    assert not loop.ragged and loop.live_rows == 0 and len(loop._graphs) == 2
     loop.ragged_rows_pay = lambda *a: False             # same chain, padded rows
     torch.manual_seed(1)
     xb, hb = model.sample_padded(small, dev())
