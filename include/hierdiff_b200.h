@@ -18,7 +18,7 @@
  *   - tensors are fp32, row-major, in the reference's padded layout: z/eps [B,N,3+F],
  *     h [B*N,*], x [B*N,3]; masks are given as `sizes[b]` = number of real nodes of
  *     molecule b (node_mask[b,i] = i < sizes[b]; edge_mask[b,i,j] = i,j < sizes[b], i != j;
- *     diffusion_qm9.py:350-359).
+ *     diffusion_qm9.py:350-359), 1 <= sizes[b] <= N (the reference's size histogram has no empty molecule).
  */
 #ifndef HIERDIFF_B200_H
 #define HIERDIFF_B200_H
