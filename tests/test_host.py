@@ -227,3 +227,31 @@ def test_merged_sample_batches_bookkeeping(tmp_path):
         c = [0.5, -2.0][(k // 4) % 2]
         assert torch.all(r["x"] == want[k]) and torch.all(r["h"] == c) and torch.all(r["context"] == c)
         assert r["h"].shape == (want[k], 8) and r["context"].shape == (want[k], 1)
+
+
+def test_argument_checks_of_the_ragged_entry_point_need_no_gpu():
+    """hd_dynamics_forward_ragged validates its shape arguments before touching the device: a bound outside
+    [0, B*N], more than 4096 molecules on a tensor-core engine or N > 128 return HD_E_INVALID with a message."""
+    from hierdiff_b200 import native
+    L = native.lib()
+    hc = native.HdConfig(1, 2, 256, 9, 1, 1, 30.0, 0.0, 10.0, 0)   # EGNN(n_layers=1, ...) as egnn.hd_config() builds it
+    one = ctypes.c_void_p(16)   # never dereferenced: every call below fails validation first
+
+    def call(B, N, live, engine=native.ENGINE_TC_STRICT):
+        return L.hd_dynamics_forward_ragged(ctypes.byref(hc), one, one, one, None, 0, one, B, N, live, one, one, None,
+                                            engine, None)
+
+    assert call(2, 3, 7) == -1 and b"live_rows" in L.hd_last_error()
+    assert call(2, 3, -1) == -1
+    assert call(2, 129, 0) == -1 and b"N" in L.hd_last_error()
+
+
+def test_ragged_rows_rule():
+    """SamplingLoop.ragged_rows_pay: the hint is set only for batches beyond one wave of node-GEMM CTAs with at least
+    a quarter of padding."""
+    from hierdiff_b200.sampling import SamplingLoop
+    pay = SamplingLoop.ragged_rows_pay
+    assert not pay([40] * 64, 64, 40)                  # headline shape: no padding
+    assert not pay([3] * 63 + [40], 64, 40)            # much padding but 2560 rows: one wave either way
+    assert pay([5] * 255 + [40], 256, 40)
+    assert not pay([35] * 256, 256, 40)                # 12 % padding only
