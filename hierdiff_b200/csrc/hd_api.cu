@@ -428,12 +428,12 @@ __global__ void final_scalars_k(const float* __restrict__ g0, int count, float* 
 }
 
 __global__ void loop_fetch_k(int32_t* counter, const float* __restrict__ t_table, const float* __restrict__ sched_table,
-                             int B, float* __restrict__ t_cur, float* __restrict__ sched_cur) {
+                             int B, int sched_rows, float* __restrict__ t_cur, float* __restrict__ sched_cur) {
   pdl_wait();
   pdl_trigger();
   const int k = *counter;
   for (int b = threadIdx.x; b < B; b += blockDim.x) t_cur[b] = t_table[k];
-  if (threadIdx.x < 3) sched_cur[threadIdx.x] = sched_table[3 * k + threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * sched_rows; i += blockDim.x) sched_cur[i] = sched_table[(int64_t)3 * sched_rows * k + i];
   __syncthreads();
   if (threadIdx.x == 0) *counter = k + 1;
 }
@@ -769,14 +769,14 @@ HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* 
   return HD_OK;
 }
 
-HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B, float* t_cur,
-                      float* sched_cur, hd_stream_t stream) {
-  if (!counter || !t_table || !sched_table || !t_cur || !sched_cur || B < 1) {
+HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B,
+                      int32_t sched_rows, float* t_cur, float* sched_cur, hd_stream_t stream) {
+  if (!counter || !t_table || !sched_table || !t_cur || !sched_cur || B < 1 || (sched_rows != 1 && sched_rows != B)) {
     set_error("bad argument");
     return HD_E_INVALID;
   }
   HD_CHECK_CUDA(launch_pdl(loop_fetch_k, dim3(1), dim3(128), 0, static_cast<cudaStream_t>(stream), counter, t_table,
-                          sched_table, B, t_cur, sched_cur));
+                          sched_table, B, sched_rows, t_cur, sched_cur));
   count_launch();
   return HD_OK;
 }

@@ -83,8 +83,8 @@ class DiffusionQM9(nn.Module):
         self.merge_batches = bool(_get(cfg, "merge_batches", False))
         self.max_chain_molecules = int(_get(cfg, "max_chain_molecules", 1024) or 1024)
         self._loops = {}
-        self._table = None
-        self._table_key = None
+        self._tables = {}         # (device, T, B) -> [ScheduleTable, version of the gamma parameters it holds]
+        self._epoch = 0
         self.last_sample_stats = {}
 
     # ------------------------------------------------------------------ configuration helpers
@@ -215,8 +215,8 @@ class DiffusionQM9(nn.Module):
         return zs
 
     @torch.no_grad()
-    def sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise=False):
-        """diffusion_qm9.py:294-310."""
+    def sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise=False, _norm=None):
+        """diffusion_qm9.py:294-310.  ``_norm``: (norm_x, norm_h, bias_h) override used by the EDM adapter."""
         if fix_noise:
             raise NotImplementedError("fix_noise is not built")
         B, N, _ = z0.shape
@@ -231,23 +231,36 @@ class DiffusionQM9(nn.Module):
         rx, rh = self._draw(B, N, z0.device)
         x = torch.empty(B, N, self.n_dims, device=z0.device)
         h = torch.empty(B, N, self.in_node_nf, device=z0.device)
+        nx, nh, bh = _norm if _norm is not None else (self.norm_values[0], self.norm_values[1], self.norm_biases[1])
         with torch.cuda.device(z0.device):
             st = native.stream_ptr()
             native.check(L.hd_final_scalars(native.ptr(gamma_0), B, native.ptr(sched), st), "hd_final_scalars")
             native.check(L.hd_final_decode(native.ptr(z0), native.ptr(eps), native.ptr(rx), native.ptr(rh),
                                            native.ptr(sizes), B, N, self.in_node_nf, native.ptr(sched), 1,
-                                           float(self.norm_values[0]), float(self.norm_values[1]),
-                                           float(self.norm_biases[1]), native.ptr(x), native.ptr(h), st),
+                                           float(nx), float(nh), float(bh), native.ptr(x), native.ptr(h), st),
                          "hd_final_decode")
         self._raise_on_flags(flags)
         return x, h
 
     # ------------------------------------------------------------------ the sampler
-    def schedule_table(self, device):
-        key = (str(device), self.T) + tuple((p.data_ptr(), p._version) for p in self.gamma.parameters())
-        if key != self._table_key:
-            self._table, self._table_key = ScheduleTable(self.gamma, self.T, device), key
-        return self._table
+    def mark_weights_changed(self):
+        """Call after writing parameters through ``.data`` (which does not bump autograd versions), e.g.
+        ``parallel.broadcast_parameters``: the packed weight image and the schedule tables are rebuilt on next use."""
+        self._epoch += 1
+        self.dynamics.egnn.mark_weights_changed()
+
+    def schedule_table(self, device, B):
+        """The [T+1, B] schedule of a B-molecule chain on ``device`` (refilled in place when gamma's parameters
+        changed, so captured graphs keep valid addresses)."""
+        key = (str(device), self.T, B)
+        ver = (self._epoch,) + tuple((p.data_ptr(), p._version) for p in self.gamma.parameters())
+        hit = self._tables.get(key)
+        if hit is None:
+            self._tables[key] = hit = [ScheduleTable(self.gamma, self.T, B, device), ver]
+        elif hit[1] != ver:
+            hit[0].refill(self.gamma)
+            hit[1] = ver
+        return hit[0]
 
     def sampling_loop(self, B, N, device):
         key = (B, N, str(device), self.engine, self.use_cuda_graph, self.steps_per_graph)
@@ -255,7 +268,7 @@ class DiffusionQM9(nn.Module):
             self._loops[key] = SamplingLoop(self, B, N, device, steps_per_graph=self.steps_per_graph,
                                             use_graph=self.use_cuda_graph)
         loop = self._loops[key]
-        loop.prepare(self.schedule_table(device))
+        loop.prepare(self.schedule_table(device, B))
         return loop
 
     @torch.no_grad()
@@ -301,6 +314,10 @@ class DiffusionQM9(nn.Module):
                     "PRO", "SER", "THR", "TRP", "TYR", "VAL"]
 
     def _check_pocket_cond(self, pocket_cond, num_samples):
+        if self.dynamics.egnn.aggregation_method != "sum":
+            # 'mean' divides by the dense edge count per row (egnn_new.py:283-288), which includes the pocket columns:
+            # the ligand-only chain would not reproduce it
+            raise NotImplementedError("pocket conditioning is built for aggregation_method='sum' only")
         if not self.pocket:
             raise ValueError("pocket_cond given but the model was built with cfg.pocket = False")
         if len(pocket_cond) != 4:
@@ -356,6 +373,10 @@ class DiffusionQM9(nn.Module):
         in the reference's order, then the pool is sorted by size, cut into chains of at most
         ``max_chain_molecules`` and the results are put back in batch order.  Molecules are independent
         (SURVEY 8e), so this is the same sampler; only the noise stream is consumed in a different shape."""
+        if self.dynamics.egnn.aggregation_method != "sum":
+            # 'mean' normalises by the padded row length N of the batch a molecule sits in (egnn_new.py:283-288):
+            # pooling changes N, hence the result
+            raise NotImplementedError("merge_batches is built for aggregation_method='sum' only")
         sizes, ctx_vals, test_names = [], [], []
         for i in range(num_batches):
             if cond_all is not None:

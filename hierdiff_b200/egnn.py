@@ -129,6 +129,7 @@ class EGNN(nn.Module):
         self.engine = "strict"   # 'fp32' | 'strict' | 'fast' (see include/hierdiff_b200.h HD_ENGINE_*)
         self._packed = None
         self._packed_key = None
+        self._epoch = 0          # bumped by mark_weights_changed(): in-place `.data` writes do not touch `_version`
         self._ws = {}
 
     # ------------------------------------------------------------------ native plumbing
@@ -141,10 +142,17 @@ class EGNN(nn.Module):
         """Parameters in state_dict order == the flat buffer order of ``hd_weight_count``."""
         return [p for _, p in self.named_parameters()]
 
+    def mark_weights_changed(self):
+        """Call after writing parameters through ``.data`` (no autograd version bump), e.g. a weight broadcast."""
+        self._epoch += 1
+
     def packed_weights(self):
-        """Kernel-ready weight image on the parameters' device (rebuilt when any parameter changed)."""
+        """Kernel-ready weight image on the parameters' device, re-packed when any parameter changed.
+
+        The image is rebuilt INTO THE SAME device buffer whenever its size and device allow, so captured CUDA graphs
+        (which embed its address) keep working across ``load_state_dict`` / weight broadcasts."""
         params = self.flat_parameters()
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (self._epoch,) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self._packed_key:
             dev = params[0].device
             if dev.type != "cuda":
@@ -158,7 +166,9 @@ class EGNN(nn.Module):
                 raise native.NativeError(native.last_error())
             assert flat.numel() == n, (flat.numel(), n)
             nbytes = L.hd_packed_bytes(cfg)
-            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            packed = self._packed
+            if packed is None or packed.device != dev or packed.numel() != nbytes:
+                packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
                 native.check(L.hd_pack_weights(cfg, native.ptr(flat), native.ptr(packed), native.stream_ptr()),
                              "hd_pack_weights")

@@ -42,7 +42,7 @@ class EnVariationalDiffusion(DiffusionQM9):
             self.check_issues_norm_values()
         self.pocket = False
         self.steps_per_graph, self.use_cuda_graph = 8, True
-        self._loops, self._table, self._table_key = {}, None, None
+        self._loops, self._tables, self._epoch = {}, {}, 0
 
     def phi(self, x, t, node_mask, edge_mask, context):
         return self.dynamics._forward(t, x, node_mask, edge_mask, context)
@@ -62,12 +62,9 @@ class EnVariationalDiffusion(DiffusionQM9):
 
     def sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise=False):
         """en_diffusion.py:346-368."""
-        nv, nb = self.norm_values, self.norm_biases
-        try:   # the shared kernel applies one (scale, bias) to every feature channel: take them raw, finish here
-            self.norm_values, self.norm_biases = (nv[0], 1.0, 1.0), (nb[0], 0.0, 0.0)
-            x, z_h = DiffusionQM9.sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise)
-        finally:
-            self.norm_values, self.norm_biases = nv, nb
+        # the shared kernel applies one (scale, bias) to every feature channel: take them raw, finish here
+        x, z_h = DiffusionQM9.sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise,
+                                                   _norm=(self.norm_values[0], 1.0, 0.0))
         return x, self._to_edm_h(z_h, node_mask)
 
     @torch.no_grad()
@@ -80,12 +77,7 @@ class EnVariationalDiffusion(DiffusionQM9):
         node_mask = node_mask.reshape(n_samples, n_nodes, 1)
         sizes = self._masks_to_sizes(node_mask, edge_mask)
         loop = self.sampling_loop(n_samples, n_nodes, device)
-        nv, nb = self.norm_values, self.norm_biases
-        try:
-            self.norm_values, self.norm_biases = (nv[0], 1.0, 1.0), (nb[0], 0.0, 0.0)
-            x, z_h, flags = loop.run(sizes.cpu(), context=context)
-        finally:
-            self.norm_values, self.norm_biases = nv, nb
+        x, z_h, flags = loop.run(sizes.cpu(), context=context, norm=(self.norm_values[0], 1.0, 0.0))
         x, z_h = x.clone(), z_h.clone()
         self._raise_on_flags(flags)
         h = self._to_edm_h(z_h, node_mask != 0)

@@ -51,6 +51,8 @@ def broadcast_parameters(module, ctx, src=0):
         n = t.numel()
         t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
         off += n
+    if hasattr(module, "mark_weights_changed"):   # `.data` writes bump no autograd version: tell the packers
+        module.mark_weights_changed()
     return flat.numel() * 4
 
 

@@ -9,6 +9,7 @@ pickles ``(results, test_names)`` - the tuple ``generation/ar_sampling_nosize.py
 Under ``torchrun`` the batches are sharded over ranks (parallel.py) and rank 0 writes the merged pickle.
 """
 import argparse
+import io
 import pickle
 
 import torch
@@ -21,11 +22,75 @@ def init_model(cfg):
     return instantiate(cfg.model, cfg=cfg, _recursive_=False)
 
 
-def load_checkpoint(model, path):
-    state = torch.load(path, map_location="cpu")["state_dict"]
+class _Opaque:
+    """Placeholder for any non-tensor object pickled into a checkpoint (accepts whatever pickle does to it)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Opaque()
+
+    def __setstate__(self, state):
+        pass
+
+    def __setitem__(self, k, v):
+        pass
+
+    def __getattr__(self, name):       # append / extend / update ... on rebuilt containers
+        return _Opaque()
+
+
+class _TensorsOnlyUnpickler(pickle.Unpickler):
+    """Unpickles torch tensors and plain containers; every other global becomes an inert placeholder.
+
+    The reference's checkpoint is a pytorch-lightning file whose ``hyper_parameters`` entry is an OmegaConf
+    ``DictConfig`` (``save_hyperparameters()``, diffusion_qm9.py:40): ``torch.load(weights_only=True)`` rejects it and
+    ``weights_only=False`` needs omegaconf / pytorch_lightning installed.  sampler.py:26-34 reads ``['state_dict']``
+    only, so only tensors are materialised here."""
+
+    _SAFE = {("collections", "OrderedDict"), ("torch._utils", "_rebuild_tensor_v2"),
+             ("torch._utils", "_rebuild_parameter"), ("torch", "Size"), ("torch", "device"),
+             ("torch.serialization", "_get_layout"), ("builtins", "set"), ("builtins", "frozenset"),
+             ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "int"),
+             ("builtins", "float"), ("builtins", "str"), ("builtins", "bool")}
+
+    def find_class(self, module, name):
+        if (module, name) in self._SAFE or (module == "torch" and name.endswith(("Storage", "Tensor"))) or \
+                (module == "torch" and name in _TORCH_DTYPES):
+            return super().find_class(module, name)
+        return _Opaque
+
+
+_TORCH_DTYPES = {n for n in dir(torch) if isinstance(getattr(torch, n), torch.dtype)}
+
+
+class _pickle_shim:
+    """The ``pickle_module`` torch.load expects, with the restricted Unpickler."""
+    __name__ = "pickle"
+    Unpickler = _TensorsOnlyUnpickler
+    load = staticmethod(lambda f, **k: _TensorsOnlyUnpickler(f, **k).load())
+    loads = staticmethod(lambda b, **k: _TensorsOnlyUnpickler(io.BytesIO(b), **k).load())
+    dumps, dump, UnpicklingError, PicklingError = pickle.dumps, pickle.dump, pickle.UnpicklingError, pickle.PicklingError
+
+
+def read_state_dict(path):
+    """``ckpt['state_dict']`` of a (lightning) checkpoint with the ``model.`` prefix stripped (sampler.py:26-32).
+
+    Tries the safe ``weights_only=True`` load first; a checkpoint carrying non-tensor objects (lightning
+    hyper-parameters) is re-read with an unpickler that materialises tensors only."""
+    try:
+        ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError:
+        ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_pickle_shim)
+    state = ckpt["state_dict"]
     for key in list(state):
         state[key.replace("model.", "")] = state.pop(key)
-    model.load_state_dict(state)
+    return state
+
+
+def load_checkpoint(model, path):
+    model.load_state_dict(read_state_dict(path))
 
 
 def main(argv=None):

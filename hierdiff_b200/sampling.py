@@ -13,37 +13,58 @@ import os
 import torch
 
 from . import native
+from .noise_model import PredefinedNoiseSchedule
 
 
 class ScheduleTable:
-    """gamma(t) and the per-step scalars of diffusion_qm9.py:181-204,:320-334 for all T steps.
+    """gamma(t) and the per-step scalars of diffusion_qm9.py:181-204,:320-334 for all T steps of a B-molecule chain.
 
-    Row k < T belongs to the k-th executed step (s = T-1-k, t = s+1); row T holds the final-decode
-    scalars {alpha_0, sigma_0, sigma_x} of diffusion_qm9.py:294-304 and time 0.
+    The reference evaluates ``gamma`` twice per step on a ``[B,1]`` tensor (``sample_p_zs_given_zt``,
+    diffusion_qm9.py:314-315, called with ``s_array`` / ``t_array`` of :376-379) and every molecule uses ITS row of the
+    result.  ``GammaNetwork`` is a small MLP whose rounding depends on the call shape (2.7e-4 between a
+    ``[T+1,1]`` grid and ``[B,1]`` calls), so the table is built from T+1 calls of exactly that shape on the sampling
+    device - ``gamma(full((B,1), k) / T)`` for k = 0..T; step s reads rows s and s+1, the final decode row 0
+    (diffusion_qm9.py:296-297: ``gamma(zeros(B,1))``) - and keeps one row of scalars PER MOLECULE.
+
+    Row k < T of ``sched`` [T+1,B,3] belongs to the k-th executed step (s = T-1-k, t = s+1); row T holds the
+    final-decode scalars {alpha_0, sigma_0, sigma_x} of diffusion_qm9.py:294-304.  ``t`` [T+1] is the time fed to the
+    dynamics (t/T for the steps, 0 for the final decode).
+
+    ``refill`` recomputes the values INTO THE SAME device tensors, so CUDA graphs that captured their addresses stay
+    valid when the schedule's parameters change (load_state_dict, a weight broadcast).
     """
 
-    def __init__(self, gamma_module, T, device):
-        L = native.lib()
-        self.T = T
-        with torch.no_grad():
-            # the reference evaluates gamma on s/T and (s+1)/T, int64 / int -> fp32 true division (:376-379)
-            grid = (torch.arange(T + 1, device=device) / T).view(-1, 1)
-            gamma = gamma_module(grid).reshape(-1).float().contiguous()   # gamma[k] = gamma(k/T)
-        self.gamma = gamma
-        order = torch.arange(T - 1, -1, -1, device=device)
-        g_s = gamma[order].contiguous()
-        g_t = gamma[order + 1].contiguous()
-        self.sched = torch.empty(T + 1, 3, dtype=torch.float32, device=device)
+    def __init__(self, gamma_module, T, B, device):
+        self.T, self.B, self.device = T, B, torch.device(device)
+        self.gamma = torch.empty(T + 1, B, dtype=torch.float32, device=device)    # gamma[k, b] = gamma(k/T) row b
+        self.sched = torch.empty(T + 1, B, 3, dtype=torch.float32, device=device)
         self.t = torch.empty(T + 1, dtype=torch.float32, device=device)
-        self.t[:T] = grid.view(-1)[order + 1]
+        self.refill(gamma_module)
+
+    @torch.no_grad()
+    def refill(self, gamma_module):
+        L, T, B, device = native.lib(), self.T, self.B, self.device
+        if isinstance(gamma_module, PredefinedNoiseSchedule):
+            # PredefinedNoiseSchedule is a table lookup (noise_model.py:155-160): no arithmetic, no shape dependence
+            grid = (torch.arange(T + 1, device=device) / T).view(-1, 1)
+            self.gamma.copy_(gamma_module(grid).reshape(-1, 1).float().expand(T + 1, B))
+        else:
+            for k in range(T + 1):
+                # int64 fill / int -> fp32 true division, as diffusion_qm9.py:376-379
+                arr = torch.full((B, 1), fill_value=k, device=device) / T
+                self.gamma[k].copy_(gamma_module(arr).reshape(-1))
+        order = torch.arange(T - 1, -1, -1, device=device)
+        g_s = self.gamma[order].contiguous()          # [T,B]
+        g_t = self.gamma[order + 1].contiguous()
+        self.t[:T] = (torch.arange(T + 1, device=device) / T)[order + 1]
         self.t[T] = 0.0
         with torch.cuda.device(device):
             st = native.stream_ptr()
-            native.check(L.hd_step_scalars(native.ptr(g_s), native.ptr(g_t), T, native.ptr(self.sched), st),
+            native.check(L.hd_step_scalars(native.ptr(g_s), native.ptr(g_t), T * B, native.ptr(self.sched), st),
                          "hd_step_scalars")
-            native.check(L.hd_final_scalars(native.ptr(gamma[:1].contiguous()), 1,
-                                            self.sched[T].data_ptr(), st), "hd_final_scalars")
-            torch.cuda.current_stream().synchronize()
+            native.check(L.hd_final_scalars(native.ptr(self.gamma[0]), B, self.sched[T].data_ptr(), st),
+                         "hd_final_scalars")
+            torch.cuda.current_stream().synchronize()   # g_s / g_t are freed on return
 
 
 class SamplingLoop:
@@ -59,7 +80,7 @@ class SamplingLoop:
         self.rx = torch.zeros(B, N, 3, **f32)
         self.rh = torch.zeros(B, N, self.F, **f32)
         self.t_cur = torch.zeros(B, **f32)
-        self.sched_cur = torch.zeros(3, **f32)
+        self.sched_cur = torch.zeros(B, 3, **f32)     # this step's scalars, one row per molecule
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
         self.flags = torch.zeros(1, dtype=torch.int32, device=device)
         self.sizes = torch.full((B,), N, dtype=torch.int32, device=device)
@@ -73,6 +94,7 @@ class SamplingLoop:
         self.ragged = False        # HD_ENGINE_RAGGED_ROWS hint of the current sizes (see ragged_rows_pay)
         self.live_rows = 0         # with the hint: sum(sizes) rounded up to whole 128-row tiles (sizes the node grids)
         self._graphs = {}          # (hint, live_rows) -> captured graph (both are baked into the captured launches)
+        self._captured_ptrs = None # device addresses the captured launches embed (packed weights, schedule table)
         self.graph_steps = 0
         self.launches_per_step = None
 
@@ -91,29 +113,32 @@ class SamplingLoop:
         L, m = native.lib(), self.model
         st = native.stream_ptr()
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
-                                     self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
+                                     self.B, self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st),
+                     "hd_loop_fetch")
         m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
                                  ragged=self.ragged, live_rows=self.live_rows)
         self.rx.normal_()
         self.rh.normal_()
         native.check(L.hd_reverse_step(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
                                        native.ptr(self.rh), native.ptr(self.sizes), self.B, self.N, self.F,
-                                       native.ptr(self.sched_cur), 0, native.ptr(self.z), native.ptr(self.flags),
+                                       native.ptr(self.sched_cur), 1, native.ptr(self.z), native.ptr(self.flags),
                                        st), "hd_reverse_step")
 
-    def _final(self):
+    def _final(self, norm=None):
+        """``norm``: (norm_x, norm_h, bias_h) of ``unnormalize`` (diffusion_qm9.py:174-179); default: the model's."""
         L, m = native.lib(), self.model
         st = native.stream_ptr()
         native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
-                                     self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st), "hd_loop_fetch")
+                                     self.B, self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st),
+                     "hd_loop_fetch")
         m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
                                  ragged=self.ragged, live_rows=self.live_rows)
         self.rx.normal_()
         self.rh.normal_()
-        nv, nb = m.norm_values, m.norm_biases
+        nx, nh, bh = norm if norm is not None else (m.norm_values[0], m.norm_values[1], m.norm_biases[1])
         native.check(L.hd_final_decode(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
                                        native.ptr(self.rh), native.ptr(self.sizes), self.B, self.N, self.F,
-                                       native.ptr(self.sched_cur), 0, float(nv[0]), float(nv[1]), float(nb[1]),
+                                       native.ptr(self.sched_cur), 1, float(nx), float(nh), float(bh),
                                        native.ptr(self.x_out), native.ptr(self.h_out), st), "hd_final_decode")
 
     def _capture(self, k):
@@ -140,6 +165,13 @@ class SamplingLoop:
     def prepare(self, table):
         """Bind the schedule table and (re)capture the graph; not part of a sample's timed region."""
         self.table = table
+        # captured launches hold raw device addresses: a reallocated weight image or schedule table (the model moved
+        # to another device, a different configuration) invalidates every graph of this loop.  Plain weight updates
+        # do not: they are repacked / refilled into the same buffers.
+        ptrs = (self.model.dynamics.egnn.packed_weights().data_ptr(), table.t.data_ptr(), table.sched.data_ptr())
+        if ptrs != self._captured_ptrs:
+            self._graphs.clear()
+            self._captured_ptrs = ptrs
         if self.use_graph and self.graph is None:
             k = self.steps_per_graph
             while k > 1 and table.T % k:
@@ -147,17 +179,21 @@ class SamplingLoop:
             with torch.cuda.device(self.device):
                 self._capture(k)
 
-    def run(self, sizes_host, z_T=None, context=None):
+    def run(self, sizes_host, z_T=None, context=None, norm=None):
         """Run the whole chain; returns padded (x [B,N,3], h [B,N,F]) on the device and the status word."""
         T = self.table.T
         if (context is None) != (self.context is None):
             raise ValueError("context must be given exactly when the dynamics has context_node_nf > 0")
         sizes_list = sizes_host.tolist() if hasattr(sizes_host, "tolist") else list(sizes_host)
+        if len(sizes_list) != self.B or min(sizes_list) < 1 or max(sizes_list) > self.N:
+            raise ValueError(f"sizes must be {self.B} values in [1, {self.N}]")
         self.ragged = self.ragged_rows_pay(sizes_list, self.B, self.N)
         self.live_rows = -(-int(sum(sizes_list)) // 128) * 128 if self.ragged else 0
+        with torch.cuda.device(self.device):
+            # sizes first: a first capture with this hint warms up on them (live_rows is a bound on THEIR sum)
+            self.sizes.copy_(torch.as_tensor(sizes_host, dtype=torch.int32), non_blocking=True)
         self.prepare(self.table)        # first chain with this hint: capture its graph
         with torch.cuda.device(self.device):
-            self.sizes.copy_(torch.as_tensor(sizes_host, dtype=torch.int32), non_blocking=True)
             if context is not None:
                 self.context.copy_(torch.as_tensor(context, dtype=torch.float32).expand_as(self.context),
                                    non_blocking=True)
@@ -185,7 +221,7 @@ class SamplingLoop:
                 done += 1
             if nvtx:
                 torch.cuda.nvtx.range_push("hierdiff.final_decode")
-            self._final()
+            self._final(norm)
             if nvtx:
                 torch.cuda.nvtx.range_pop()
                 torch.cuda.nvtx.range_pop()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 3
+#define HD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -170,10 +170,12 @@ HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* 
 
 /* Graph-replay helpers for the T-step loop (diffusion_qm9.py:375-384).  A captured step
  * reads its time and schedule scalars through a device-side step counter so ONE captured
- * graph serves all T steps:  hd_loop_fetch copies t_table[*counter] into t_cur[0..B) and
- * sched_table[*counter][0..3) into sched_cur[0..3), then increments *counter. */
+ * graph serves all T steps:  hd_loop_fetch copies t_table[*counter] into t_cur[0..B) and row *counter of
+ * sched_table [T+1][sched_rows][3] into sched_cur [sched_rows][3], then increments *counter.  sched_rows is B (one
+ * row of scalars per molecule, as the reference computes them from its [B,1] gamma calls, diffusion_qm9.py:314-334;
+ * pass sched_per_mol = 1 to hd_reverse_step / hd_final_decode) or 1 (one row for the whole batch). */
 HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B,
-                      float* t_cur, float* sched_cur, hd_stream_t stream);
+                      int32_t sched_rows, float* t_cur, float* sched_cur, hd_stream_t stream);
 
 /* Profiling hook: enqueue ONLY the fused edge kernel of sub-layer (block, sub) - sub == inv_sublayers selects
  * the EquivariantUpdate - on the operands a previous hd_gcl_forward / hd_equiv_update call left in `workspace`

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Generate the golden fixtures in this directory from the UNMODIFIED reference.
 
-Runs only where /root/reference exists (the build container).  It imports the
-reference's hot-path modules as they are: two stub
-modules stand in for ``pytorch_lightning`` and ``hydra`` (absent in this
+Runs where the reference is available: /root/reference (the build container) or its staged hot-path copy
+``oracle/_ref`` (``oracle/stage_ref.py``).  ``oracle/ref_runner.py`` imports the reference's modules as they are
+(SURVEY.md section 8c): two stub modules stand in for ``pytorch_lightning`` and ``hydra`` (absent in this
 image), the model cfg is the reference's own ``conf/model/ddpmgblur.yaml``,
 weights come from ``weightgen.py`` and are loaded with ``load_state_dict``.
 
@@ -26,93 +26,17 @@ import torch.nn as nn
 import yaml
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = "/root/reference/endiffusion"
 sys.path.insert(0, HERE)
 from weightgen import fill_state_dict  # noqa: E402
 
 
 # ----------------------------------------------------------------------------
-# reference import with stubs
+# reference import with stubs: oracle/ref_runner.py (staged copy under oracle/_ref, else /root/reference)
 # ----------------------------------------------------------------------------
-def _install_stubs():
-    pl = types.ModuleType("pytorch_lightning")
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.ref_runner import FixedNodes, make_reference, root as _ref_root  # noqa: E402
 
-    class LightningModule(nn.Module):
-        def save_hyperparameters(self, *a, **k):
-            pass
-
-        def log(self, *a, **k):
-            pass
-
-    pl.LightningModule = LightningModule
-    sys.modules["pytorch_lightning"] = pl
-    hydra = types.ModuleType("hydra")
-    hutils = types.ModuleType("hydra.utils")
-    hutils.instantiate = lambda *a, **k: None
-    hydra.utils = hutils
-    sys.modules["hydra"] = hydra
-    sys.modules["hydra.utils"] = hutils
-
-
-class AttrDict(dict):
-    """attr + item access, like the OmegaConf node the reference receives."""
-
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
-
-    def __setattr__(self, k, v):
-        self[k] = v
-
-
-def to_attr(d):
-    if isinstance(d, dict):
-        return AttrDict({k: to_attr(v) for k, v in d.items()})
-    return d
-
-
-class FixedNodes(nn.Module):
-    def __init__(self, sizes):
-        super().__init__()
-        self.sizes = list(sizes)
-
-    def sample(self, k):
-        assert k == len(self.sizes)
-        return list(self.sizes)
-
-
-def make_reference(n_layers, timesteps, seed=2022, noise_schedule="learned", context_node_nf=0, pocket=False):
-    _install_stubs()
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    import contextlib
-    import io
-
-    from train_module.diffusion_qm9 import DiffusionQM9
-
-    cfg = to_attr(yaml.safe_load(open(os.path.join(REF, "conf/model/ddpmgblur.yaml")))["cfg"])
-    cfg.dynamics.n_layers = n_layers
-    cfg.dynamics.context_node_nf = context_node_nf
-    cfg.pocket = pocket
-    cfg.timesteps = timesteps
-    cfg.noise_schedule = noise_schedule
-    if noise_schedule != "learned":
-        cfg.pre_noise = to_attr({"noise_schedule": noise_schedule, "timesteps": timesteps,
-                                 "precision": 1e-4})
-        cfg.loss_type = "l2"
-    cfg.analyze = os.path.join(REF, "conf/analyze/GEOM.yaml")
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = DiffusionQM9(cfg)
-    model.cwd = ""
-    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
-    sd = {k: torch.from_numpy(v) for k, v in fill_state_dict(shapes, seed).items()}
-    if noise_schedule != "learned":
-        sd["gamma.gamma"] = model.state_dict()["gamma.gamma"]
-    model.load_state_dict(sd)
-    model.eval()
-    return model
+REF = _ref_root()
 
 
 def masks_for(sizes, N):
@@ -222,6 +146,65 @@ def case_sample(name, n_layers, T, sizes, seed, noise_schedule="learned"):
                         sample_seed=np.int32(seed))
     print(name, "x absmax", float(np.abs(x).max()), "h absmax", float(np.abs(hh).max()),
           "z_traj absmax", float(np.abs(np.stack(zs)).max()))
+
+
+def draws_digest(nx, nh):
+    """What the T=1000 test checks before trusting draws it regenerated from the seed."""
+    return np.array([nx.astype(np.float64).sum(), nh.astype(np.float64).sum(),
+                     np.abs(nx).astype(np.float64).sum(), np.abs(nh).astype(np.float64).sum()])
+
+
+def case_sample_long(name="sample_t1000_b2", n_layers=4, T=1000, sizes=(40, 40), seed=0, keep_every=100):
+    """configs[1]'s model and chain length at a small batch: the full T=1000 reference chain on CPU.  The 2*(T+2)
+    randn draws are NOT stored (3.5 MB of noise): the CPU generator reproduces them from ``sample_seed`` (same torch
+    build in the test image); a digest guards that.  z_t is kept every ``keep_every`` steps."""
+    model = make_reference(n_layers, T)
+    sizes = list(sizes)
+    model.nodes_dist = FixedNodes(sizes)
+    B, N = len(sizes), max(sizes)
+    draws, gam, zs = [], [], []
+    real_randn = torch.randn
+
+    def rec_randn(*a, **k):
+        v = real_randn(*a, **k)
+        draws.append(v.clone().numpy())
+        return v
+
+    h = model.gamma.register_forward_hook(lambda m, i, o: gam.append(o.detach().clone().numpy()[:, 0]))
+    real_step = model.sample_p_zs_given_zt
+
+    def rec_step(*a, **k):
+        v = real_step(*a, **k)
+        zs.append(v.clone().numpy())
+        return v
+
+    model.sample_p_zs_given_zt = rec_step
+    torch.manual_seed(seed)
+    torch.randn = rec_randn
+    try:
+        res = model.sample(B, torch.device("cpu"))
+    finally:
+        torch.randn = real_randn
+    h.remove()
+    assert len(draws) == 2 * (T + 2) and len(gam) == 2 * T + 1
+    nx, nh = np.stack(draws[0::2]), np.stack(draws[1::2])
+    # the regeneration recipe of the test, checked here against what the reference actually drew
+    torch.manual_seed(seed)
+    again = [torch.randn(B, N, 3 if k % 2 == 0 else 8).numpy() for k in range(2 * (T + 2))]
+    assert all(np.array_equal(a, b) for a, b in zip(again, draws))
+    # kept in consecutive pairs (k-1, k) so that single steps can be checked from a recorded state as well
+    keep = sorted(set([k - d for k in range(keep_every, T, keep_every) for d in (0, 1)] + [0, T - 2, T - 1]))
+    x = np.zeros((B, N, 3), np.float32)
+    hh = np.zeros((B, N, 8), np.float32)
+    for i, r in enumerate(res):
+        x[i, :sizes[i]] = r["x"].numpy()
+        hh[i, :sizes[i]] = r["h"].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), gamma_out=np.stack(gam), kept_steps=np.array(keep, np.int32),
+                        z_kept=np.stack([zs[k] for k in keep]).astype(np.float32), x=x, h=hh,
+                        sizes=np.array(sizes, np.int32), T=np.int32(T), n_layers=np.int32(n_layers),
+                        weight_seed=np.int32(2022), sample_seed=np.int32(seed), draws_digest=draws_digest(nx, nh),
+                        first_draw_x=nx[0], last_draw_h=nh[-1])
+    print(name, "x absmax", float(np.abs(x).max()), "z absmax", float(np.abs(np.stack(zs)).max()))
 
 
 def case_context(name="context_l1", n_layers=1, T=6, sizes=(6, 9, 2), seed=3, context=0.7):
@@ -374,6 +357,7 @@ if __name__ == "__main__":
     case_sample("sample_c1", n_layers=6, T=50, sizes=[20, 20, 20, 20], seed=0)
     case_sample("sample_ragged_l9", n_layers=9, T=20, sizes=[10, 6, 9], seed=1)
     case_sample("sample_poly_l1", n_layers=1, T=10, sizes=[4, 8], seed=2, noise_schedule="polynomial_2")
+    case_sample_long()
     case_context()
     case_pocket()
     case_gamma()

@@ -64,3 +64,24 @@ def random_batch(B, N, sizes, seed, F=8):
                          rng.standard_normal((B, N, F)).astype(np.float32), sizes)
     t = rng.uniform(0, 1, B).astype(np.float32)
     return z, t
+
+
+def regenerate_draws(g):
+    """The 2*(T+2) ``torch.randn`` draws of a reference chain whose fixture stores only the seed (sample_t1000_b2):
+    [x_T, h_T, (x, h) per step, (x, h) of the final decode] from the CPU generator, checked against the fixture's
+    digest and its first / last recorded draw.  Returns randn_x [T+2,B,N,3], randn_h [T+2,B,N,8]."""
+    T, sizes = int(g["T"]), g["sizes"]
+    B, N = len(sizes), int(sizes.max())
+    saved = torch.get_rng_state()
+    try:
+        torch.manual_seed(int(g["sample_seed"]))
+        draws = [torch.randn(B, N, 3 if k % 2 == 0 else 8).numpy() for k in range(2 * (T + 2))]
+    finally:
+        torch.set_rng_state(saved)
+    nx, nh = np.stack(draws[0::2]), np.stack(draws[1::2])
+    digest = np.array([nx.astype(np.float64).sum(), nh.astype(np.float64).sum(),
+                       np.abs(nx).astype(np.float64).sum(), np.abs(nh).astype(np.float64).sum()])
+    if not (np.array_equal(nx[0], g["first_draw_x"]) and np.array_equal(nh[-1], g["last_draw_h"])
+            and np.allclose(digest, g["draws_digest"], rtol=1e-12, atol=0)):
+        raise AssertionError("this torch build's CPU generator does not reproduce the fixture's randn draws")
+    return nx, nh

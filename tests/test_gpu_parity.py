@@ -119,6 +119,56 @@ def test_forward_matches_oracle(models, engine, n_layers, sizes, N):
     assert rel(got, want) < FWD_TOL[engine]
 
 
+# BASELINE.json's own shapes against the CPU oracle (one oracle forward per case, shared by the three engines):
+#   configs[1]  B=64,  N=40 (all real), L=4            configs[4]  B=64, GEOM-histogram sizes, L=9
+#   configs[2]  B=128, N=16 and N=56 (the two ends of the node-count sweep), ragged sizes, L=4
+def _geom_sizes(B, seed):
+    g = np.load(os.path.join(GOLDEN, "nodes_dist.npz"))
+    keys, cnt = g["hist_keys"].astype(np.int64), g["hist_counts"].astype(np.float64)
+    return np.random.default_rng(seed).choice(keys, size=B, p=cnt / cnt.sum()).astype(np.int32)
+
+
+def _baseline_case(name):
+    if name == "configs1":
+        L, sizes = 4, np.full(64, 40, np.int32)
+    elif name == "configs4_geom9":
+        L, sizes = 9, _geom_sizes(64, 4)
+    elif name == "configs2_n16":
+        L, sizes = 4, np.random.default_rng(16).integers(1, 17, 128).astype(np.int32)
+        sizes[:8] = 16
+    elif name == "configs2_n56":
+        L, sizes = 4, np.random.default_rng(56).integers(1, 57, 128).astype(np.int32)
+        sizes[:8] = 56
+    else:
+        raise KeyError(name)
+    N = int(sizes.max())
+    z, t = random_batch(len(sizes), N, sizes, seed=len(name) + N)
+    return L, sizes, N, z, t
+
+
+@pytest.fixture(scope="module")
+def oracle_baseline_cases():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            L, sizes, N, z, t = _baseline_case(name)
+            cfg, w = oracle_weights(L)
+            cache[name] = (L, sizes, N, z, t, O.dynamics_forward(cfg, w, z, t, sizes))
+        return cache[name]
+    return get
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["configs1", "configs4_geom9", "configs2_n16", "configs2_n56"])
+def test_forward_matches_oracle_at_baseline_shapes(models, oracle_baseline_cases, name, engine):
+    L, sizes, N, z, t, want = oracle_baseline_cases(name)
+    got = forward(models(L), z, t, sizes, engine)
+    assert rel(got, want) < FWD_TOL[engine], (name, engine, rel(got, want))
+    for b, n in enumerate(sizes):
+        assert np.all(got[b, n:] == 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # the diffusion update against the reference fixtures (golden draws + golden gammas injected)
 # ------------------------------------------------------------------------------------------------
@@ -218,6 +268,61 @@ def test_full_chain_matches_reference_fixture(models, engine):
                                        g["gamma_out"][2 * k], g["gamma_out"][2 * k + 1])
         scale = tol if engine != "fast" else 0.2
         assert rel(z, g["z_traj"][T - 1]) < scale, name
+
+
+@pytest.mark.parametrize("engine", ["strict", "fp32"])
+def test_t1000_chain_matches_reference_fixture(models, engine):
+    """The full T=1000 chain of configs[1]'s model (L=4, N=40; B=2) against the reference's CPU run
+    (sample_t1000_b2.npz), with the reference's draws and gamma values injected step by step: every recorded z_t along
+    the chain and the final (x, h).  With random-init weights |z| grows to 7e5 along the chain and rounding differences
+    are amplified with it; the measured deviation is recorded in gpurun_out/parity_reference.json."""
+    from helpers import regenerate_draws
+    from hierdiff_b200 import native
+    L = native.lib()
+    g = np.load(os.path.join(GOLDEN, "sample_t1000_b2.npz"))
+    T, sizes, kept = int(g["T"]), g["sizes"], list(g["kept_steps"])
+    nx, nh = regenerate_draws(g)
+    model = models(int(g["n_layers"]))
+    use(model, engine)
+    B, N = len(sizes), int(sizes.max())
+    z = cuda(masked_cog_noise(nx[0], nh[0], sizes))
+    d_sizes = cuda(sizes, torch.int32)
+    d_nx, d_nh, d_gam = cuda(nx), cuda(nh), cuda(g["gamma_out"])
+    sched = torch.empty(B, 3, device=dev())
+    flags = torch.zeros(1, dtype=torch.int32, device=dev())
+    st = native.stream_ptr()
+    worst = 0.0
+    for k in range(T):
+        s = T - 1 - k
+        t = torch.full((B,), float(np.float32(s + 1) / np.float32(T)), device=dev())
+        eps = model.dynamics.forward_sizes(t, z, d_sizes, flags=flags)
+        zs = torch.empty_like(z)
+        native.check(L.hd_step_scalars(d_gam[2 * k].data_ptr(), d_gam[2 * k + 1].data_ptr(), B, native.ptr(sched), st),
+                     "scalars")
+        native.check(L.hd_reverse_step(native.ptr(z), native.ptr(eps), d_nx[k + 1].data_ptr(), d_nh[k + 1].data_ptr(),
+                                       native.ptr(d_sizes), B, N, 8, native.ptr(sched), 1, native.ptr(zs),
+                                       native.ptr(flags), st), "reverse_step")
+        z = zs
+        if k in kept:
+            worst = max(worst, rel(z.cpu().numpy(), g["z_kept"][kept.index(k)]))
+    eps0 = model.dynamics.forward_sizes(torch.zeros(B, device=dev()), z, d_sizes, flags=flags)
+    x = torch.empty(B, N, 3, device=dev())
+    h = torch.empty(B, N, 8, device=dev())
+    native.check(L.hd_final_scalars(d_gam[2 * T].data_ptr(), B, native.ptr(sched), st), "scalars")
+    native.check(L.hd_final_decode(native.ptr(z), native.ptr(eps0), d_nx[T + 1].data_ptr(), d_nh[T + 1].data_ptr(),
+                                   native.ptr(d_sizes), B, N, 8, native.ptr(sched), 1, 1.0, 1.0, 0.0,
+                                   native.ptr(x), native.ptr(h), st), "final_decode")
+    torch.cuda.synchronize()
+    assert int(flags.item()) == 0
+    ex, eh = rel(x.cpu().numpy(), g["x"]), rel(h.cpu().numpy(), g["h"])
+    try:
+        import json
+        path = os.path.join(os.path.dirname(GOLDEN), os.pardir, "gpurun_out", f"parity_t1000_fixture_{engine}.json")
+        with open(path, "w") as f:
+            json.dump({"worst_z_along_chain": worst, "x": ex, "h": eh}, f)
+    except OSError:
+        pass
+    assert worst < 1e-3 and ex < 1e-3 and eh < 1e-3, (worst, ex, eh)
 
 
 # ------------------------------------------------------------------------------------------------

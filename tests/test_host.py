@@ -255,3 +255,60 @@ def test_ragged_rows_rule():
     assert not pay([3] * 63 + [40], 64, 40)            # much padding but 2560 rows: one wave either way
     assert pay([5] * 255 + [40], 256, 40)
     assert not pay([35] * 256, 256, 40)                # 12 % padding only
+
+
+def test_load_checkpoint_reads_a_lightning_style_file(tmp_path):
+    """sampler.py:26-34: ``torch.load(ckpt)['state_dict']`` with the ``model.`` prefix stripped.  The reference's file is
+    a lightning checkpoint whose ``hyper_parameters`` entry is an OmegaConf object (diffusion_qm9.py:40): neither
+    ``weights_only=True`` nor a plain unpickle (omegaconf is not installed) can read it; tensors must still load."""
+    import sys
+    import types
+    from hierdiff_b200.sampler import load_checkpoint, read_state_dict
+    model = make_model(tmp_path, 1)
+    other = make_model(tmp_path, 1, seed=5)
+    fake = types.ModuleType("omegaconf_like")
+
+    DictConfig = type("DictConfig", (dict,), {"__module__": "omegaconf_like", "__qualname__": "DictConfig"})
+    fake.DictConfig = DictConfig
+    sys.modules["omegaconf_like"] = fake
+    try:
+        ckpt = {"state_dict": {"model." + k: v for k, v in other.state_dict().items()},
+                "hyper_parameters": DictConfig(cfg=DictConfig(timesteps=1000)), "epoch": 7,
+                "pytorch-lightning_version": "1.4.9"}
+        path = str(tmp_path / "diffusion.ckpt")
+        torch.save(ckpt, path)
+    finally:
+        del sys.modules["omegaconf_like"]           # the class is NOT importable when the file is read
+    state = read_state_dict(path)
+    assert set(state) == set(other.state_dict())
+    load_checkpoint(model, path)
+    for k, v in other.state_dict().items():
+        assert torch.equal(model.state_dict()[k], v), k
+    plain = str(tmp_path / "plain.ckpt")             # a tensors-only file takes the weights_only=True path
+    torch.save({"state_dict": other.state_dict()}, plain)
+    assert set(read_state_dict(plain)) == set(other.state_dict())
+
+
+def test_masks_are_validated_on_every_call():
+    """utils.sizes_from_masks keeps no pointer-keyed cache: a second mask pair of the same shape (possibly at a
+    recycled address) is validated and reduced again."""
+    from hierdiff_b200.utils import masks_from_sizes, sizes_from_masks
+    nm, em = masks_from_sizes([3, 5], 5, "cpu")
+    B, N, s1 = sizes_from_masks(nm.view(10, 1), em.view(50, 1), None, 10)
+    assert (B, N, s1.tolist()) == (2, 5, [3, 5])
+    nm.copy_(masks_from_sizes([4, 1], 5, "cpu")[0])      # same storage, same shape, other content
+    em.copy_(masks_from_sizes([4, 1], 5, "cpu")[1])
+    assert sizes_from_masks(nm.view(10, 1), em.view(50, 1), None, 10)[2].tolist() == [4, 1]
+
+
+def test_staged_reference_copy_is_intact():
+    """oracle/_ref (oracle/stage_ref.py) is what the GPU parity tests and bench.py's reference legs run: when present
+    it must verify against its manifest and reproduce a committed fixture."""
+    from oracle import ref_runner, stage_ref
+    if not stage_ref.available():
+        pytest.skip("oracle/_ref not staged in this checkout (python oracle/stage_ref.py)")
+    assert stage_ref.verify()
+    g = np.load(os.path.join(GOLDEN, "sample_poly_l1.npz"))
+    ref = ref_runner.make_reference(int(g["n_layers"]), int(g["T"]), noise_schedule="polynomial_2")
+    x, h = ref_runner.sample_padded(ref, g["sizes"], "cpu", int(g["sample_seed"]))
+    assert np.array_equal(x, g["x"]) and np.array_equal(h, g["h"])

@@ -83,6 +83,30 @@ def test_final_decode_matches_reference(golden_dir, name):
     assert np.array_equal(h, g["h"])
 
 
+def test_t1000_chain_single_steps_match_reference(golden_dir):
+    """configs[1]'s model and chain length (L=4, N=40, T=1000, B=2; sample_t1000_b2.npz): the whole chain is 1001
+    forwards - minutes for the CPU oracle - so the oracle is pinned on single steps taken from recorded states spread
+    over the chain (|z| grows to 7e5 on the way), with the reference's draws and gamma values."""
+    from helpers import regenerate_draws
+    g = np.load(os.path.join(golden_dir, "sample_t1000_b2.npz"))
+    T, sizes, kept = int(g["T"]), g["sizes"], list(g["kept_steps"])
+    nx, nh = regenerate_draws(g)
+    cfg, w = weights_for(int(g["n_layers"]))
+    B = len(sizes)
+    for k in [100, 500, 900, 999]:
+        z_in = g["z_kept"][kept.index(k - 1)]
+        s = T - 1 - k
+        t = np.full(B, np.float32(s + 1) / np.float32(T), np.float32)
+        eps = O.dynamics_forward(cfg, w, z_in, t, sizes)
+        zs = O.reverse_step(z_in, eps, nx[k + 1], nh[k + 1], sizes,
+                            O.step_scalars(g["gamma_out"][2 * k], g["gamma_out"][2 * k + 1]))
+        assert rel(zs, g["z_kept"][kept.index(k)]) < 2e-5, k
+    z0 = g["z_kept"][kept.index(T - 1)]
+    eps0 = O.dynamics_forward(cfg, w, z0, np.zeros(B, np.float32), sizes)
+    x, h = O.final_decode(z0, eps0, nx[T + 1], nh[T + 1], sizes, O.final_scalars(g["gamma_out"][2 * T]))
+    assert rel(x, g["x"]) < 2e-5 and np.array_equal(h, g["h"])
+
+
 def test_full_chain_matches_reference(golden_dir):
     """Whole T-step loop, oracle end to end, injected draws (small case)."""
     g = np.load(os.path.join(golden_dir, "sample_poly_l1.npz"))
