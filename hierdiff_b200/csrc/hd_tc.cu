@@ -62,6 +62,11 @@ constexpr int NPW = 8;                // producer warps
 constexpr int NEW = 8;                // epilogue warps
 constexpr int PROD_THREADS = 32 * NPW, EPI_THREADS = 32 * NEW;
 constexpr int NTHREADS = PROD_THREADS + EPI_THREADS + 64;   // + MMA/alloc warp + metadata warp
+#ifdef HD_EXP_NO_FILL_HELP
+constexpr bool FILL_HELP = false;
+#else
+constexpr bool FILL_HELP = true;    // the epilogue warps build half of the first tile's operand chunks (pipeline fill)
+#endif
 
 struct PMeta {        // what the operand producers need of an edge row
   float r, d0;        // |x_i-x_j|^2, |x0_i-x0_j|^2
@@ -92,7 +97,12 @@ struct Params {
 
 template <bool STRICT, int CG>
 struct Smem {
-  static constexpr int W_BYTES = (CG == 2 ? 1 : 2) * W_HALF * (STRICT ? 2 : 1);
+#ifdef HD_EXP_WLO_ALIAS   // timing experiment only (wrong numerics): no resident W2 lo image, the lo pass re-reads W2 hi
+  static constexpr int W_PARTS = 1;
+#else
+  static constexpr int W_PARTS = STRICT ? 2 : 1;
+#endif
+  static constexpr int W_BYTES = (CG == 2 ? 1 : 2) * W_HALF * W_PARTS;
   static constexpr int STAGE = A_HALF * (STRICT ? 2 : 1);
   static constexpr int OFF_W = 0;
   static constexpr int OFF_A = OFF_W + W_BYTES;
@@ -104,8 +114,9 @@ struct Smem {
   static constexpr int OFF_GRP = OFF_EMETA + EMETA_BUFS * TILE_M * (int)sizeof(EMeta);   // int2 [EMETA_BUFS][16]
   static constexpr int OFF_DOT = OFF_GRP + EMETA_BUFS * 16 * 8;    // [2][TILE_M] partial attention dots
   static constexpr int OFF_BAR = OFF_DOT + 2 * TILE_M * 4;
-  // barriers: full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2], w_local, w_ready, meta, tile_start ; then tmem ptr
-  static constexpr int NBAR = 2 * NSTAGE + 8;
+  // barriers: full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2], w_local, w_ready, meta, tile_start, meta0,
+  // helper_meta ; then tmem ptr
+  static constexpr int NBAR = 2 * NSTAGE + 10;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
@@ -157,6 +168,17 @@ __device__ __forceinline__ float silu_scaled(float t) {
     return fmaf(hv, ptx::tanh_approx(hv), hv);    // = SiLU(v)
   }
 }
+// Strict mode, two elements at once: 1/(1+2^ta) and 1/(1+2^tb) from ONE reciprocal, r = 1/((1+2^ta)(1+2^tb)), as
+// r*(1+2^tb) and r*(1+2^ta) - 3 MUFU operations per pair instead of 4 (the kernel's co-bound is the MUFU pipe).
+// The exponent is clamped at 63 so that the product stays finite (2^126): beyond it SiLU(v) = v/(1+e^-v) is below
+// 5e-18 in magnitude (v < -43.6) and the clamped evaluation t * 2^-63 differs from it by less than that.
+__device__ __forceinline__ void silu_scaled_pair(float ta, float tb, float& ya, float& yb) {
+  const float da = 1.0f + ptx::ex2_approx(fminf(ta, 63.0f));
+  const float db = 1.0f + ptx::ex2_approx(fminf(tb, 63.0f));
+  const float r = ptx::rcp_approx(da * db);
+  ya = ta * (r * db);
+  yb = tb * (r * da);
+}
 // SiLU(v) = silu_kout() * silu_scaled(t)
 template <bool STRICT>
 __host__ __device__ constexpr float silu_kout() { return STRICT ? -0.6931471805599453f : 1.0f; }
@@ -192,6 +214,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   auto bar_acce = [&](int a) { return bar0 + 8u * (2 * NSTAGE + 2 + a); };
   const uint32_t bar_wl = bar0 + 8u * (2 * NSTAGE + 4), bar_wr = bar0 + 8u * (2 * NSTAGE + 5);
   const uint32_t bar_meta = bar0 + 8u * (2 * NSTAGE + 6), bar_tstart = bar0 + 8u * (2 * NSTAGE + 7);
+  // one-shot pair for the helpers of the first tile: tile 0's metadata is ready / every helper warp has read it
+  const uint32_t bar_meta0 = bar0 + 8u * (2 * NSTAGE + 8), bar_hmeta = bar0 + 8u * (2 * NSTAGE + 9);
   constexpr int MMA_WARP = NPW + NEW, META_WARP = MMA_WARP + 1;
 
   // ---- one-time setup --------------------------------------------------------------------------
@@ -216,6 +240,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     ptx::mbar_init(bar_wl, 1);
     ptx::mbar_init(bar_meta, 1);
     ptx::mbar_init(bar_tstart, NPW);
+    ptx::mbar_init(bar_meta0, 1);
+    ptx::mbar_init(bar_hmeta, NEW);
     ptx::mbar_init(bar_wr, CG);
     ptx::fence_mbar_init();
     // resident W2 image(s): this CTA's 128-row half (CG=2) or both halves (CG=1)
@@ -223,9 +249,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     const int nhalf = CG == 2 ? 1 : 2;
     for (int hf = 0; hf < nhalf; ++hf) {
       const int src_half = CG == 2 ? (int)rank : hf;
-      for (int part = 0; part < (STRICT ? 2 : 1); ++part) {
+      for (int part = 0; part < S::W_PARTS; ++part) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(part ? p.w_lo : p.w_hi) + (size_t)src_half * W_HALF;
-        const uint32_t dst = sbase + S::OFF_W + (hf * (STRICT ? 2 : 1) + part) * W_HALF;
+        const uint32_t dst = sbase + S::OFF_W + (hf * S::W_PARTS + part) * W_HALF;
         for (int off = 0; off < W_HALF; off += 16384) ptx::bulk_g2s(dst + off, src + off, 16384, bar_wl);
       }
     }
@@ -257,157 +283,230 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     ntiles = max(ntiles, (pe - pa + TILE_M - 1) / TILE_M);
   }
 
-  if (warp < NPW) {
-    // =========================== producers ===========================
-    // warp w builds rows [16w, 16w+16) of every operand stage: lane -> (row in 8-group, 4 columns of a 16-column half)
-    const int rsub = (lane >> 1) & 7;
-    const int qsub = 2 * (lane >> 4) + (lane & 1);
-    const uint32_t kcs = (uint32_t)p.kc_stride;   // floats between 16-column chunks; b_img = a_img + 16 chunks
-    // per-tile state of the 2 rows this thread feeds (16*warp + 8*rb + rsub); an 8-row group is live or dead as a whole
-    struct RowState {
-      float rr[2], dd[2];
-      uint32_t oa[2], ob[2];   // element offsets of A_i / B_j in chunk 0
-      bool ok[2];
-    };
-    auto read_meta = [&](int t, RowState& r) {
-      const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
+  // ---- operand production (the producer warps; for the first tile also the epilogue warps, see below) ----------
+  // warp pw builds rows [16 pw, 16 pw + 16) of an operand stage: lane -> (row in 8-group, 4 columns of a 16-column half)
+  const int pw = warp < NPW ? warp : warp - NPW;
+  const int rsub = (lane >> 1) & 7;
+  const int qsub = 2 * (lane >> 4) + (lane & 1);
+  const uint32_t kcs = (uint32_t)p.kc_stride;   // floats between 16-column chunks; b_img = a_img + 16 chunks
+  // per-tile state of the 2 rows this thread feeds (16*pw + 8*rb + rsub); an 8-row group is live or dead as a whole
+  struct RowState {
+    float rr[2], dd[2];
+    uint32_t oa[2], ob[2];   // element offsets of A_i / B_j in chunk 0
+    bool ok[2];
+  };
+  auto read_meta = [&](int t, RowState& r) {
+    const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
 #pragma unroll
-      for (int rb = 0; rb < 2; ++rb) {
-        const PMeta m = meta[16 * warp + 8 * rb + rsub];
-        r.rr[rb] = m.r;
-        r.dd[rb] = m.d0;
-        r.ok[rb] = m.recv >= 0;
-        r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
-        r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
-      }
-    };
-    auto load_half = [&](float4 (&v)[4], const RowState& r, int hs) {
-      const uint32_t o = hs * kcs;
+    for (int rb = 0; rb < 2; ++rb) {
+      const PMeta m = meta[16 * pw + 8 * rb + rsub];
+      r.rr[rb] = m.r;
+      r.dd[rb] = m.d0;
+      r.ok[rb] = m.recv >= 0;
+      r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
+      r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
+    }
+  };
+  auto load_half = [&](float4 (&v)[4], const RowState& r, int hs) {
+    const uint32_t o = hs * kcs;
 #pragma unroll
-      for (int rb = 0; rb < 2; ++rb) {
+    for (int rb = 0; rb < 2; ++rb) {
 #ifndef HD_EXP_NO_LDG
-        if (r.ok[rb]) {
-          v[rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[rb])));
-          v[2 + rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.ob[rb])));
-        }
-#endif
+      if (r.ok[rb]) {
+        v[rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[rb])));
+        v[2 + rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.ob[rb])));
       }
-    };
-    // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
-    // MUFU latencies of the chains overlap
-    auto half_step = [&](const float4 (&v)[4], const RowState& r, int hs, int s) {
-      const int ph = hs % HSPS;
-      const int k0 = 16 * hs + 4 * qsub;
-      const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
-      const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
-      uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8 +
-                       (16 * warp + rsub) * 16;
-      if (!(r.ok[0] || r.ok[1])) return;   // rows outside this CTA's range keep stale operand data; their
-                                           // accumulator rows are never read (group table)
-      float pre[8], m[8];
+#endif
+    }
+  };
+  // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
+  // MUFU latencies of the chains overlap
+  auto half_step = [&](const float4 (&v)[4], const RowState& r, int hs, int s) {
+    const int ph = hs % HSPS;
+    const int k0 = 16 * hs + 4 * qsub;
+    const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
+    const float4 w_d = *reinterpret_cast<const float4*>(s_wd + k0);
+    uint8_t* stage = smem + S::OFF_A + s * S::STAGE + (2 * ph + (lane >> 4)) * A_KG + (lane & 1) * 8 +
+                     (16 * pw + rsub) * 16;
+    if (!(r.ok[0] || r.ok[1])) return;   // rows outside this CTA's range keep stale operand data; their
+                                         // accumulator rows are never read (group table)
+    float pre[8], m[8];
+#if !defined(HD_EXP_NO_F32X2) && !defined(HD_EXP_NO_PAIR_RCP) && !defined(HD_EXP_NO_PROD_SILU)
+    if constexpr (STRICT) {
+      // packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): the same IEEE operations in the same order, half the issue
+      // slots.  q[2*rb], q[2*rb+1] = elements (0,1), (2,3) of row rb.
+      float2 q[4], d[4];
+      const float2 one2 = make_float2(1.0f, 1.0f);
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
         const float4 a = v[rb], b = v[2 + rb];
-        pre[4 * rb + 0] = fmaf(r.dd[rb], w_d.x, fmaf(r.rr[rb], w_r.x, a.x + b.x));
-        pre[4 * rb + 1] = fmaf(r.dd[rb], w_d.y, fmaf(r.rr[rb], w_r.y, a.y + b.y));
-        pre[4 * rb + 2] = fmaf(r.dd[rb], w_d.z, fmaf(r.rr[rb], w_r.z, a.z + b.z));
-        pre[4 * rb + 3] = fmaf(r.dd[rb], w_d.w, fmaf(r.rr[rb], w_r.w, a.w + b.w));
+        const float2 rr2 = make_float2(r.rr[rb], r.rr[rb]), dd2 = make_float2(r.dd[rb], r.dd[rb]);
+        q[2 * rb] = ptx::fma2(dd2, make_float2(w_d.x, w_d.y),
+                              ptx::fma2(rr2, make_float2(w_r.x, w_r.y), ptx::add2(make_float2(a.x, a.y), make_float2(b.x, b.y))));
+        q[2 * rb + 1] = ptx::fma2(dd2, make_float2(w_d.z, w_d.w),
+                                  ptx::fma2(rr2, make_float2(w_r.z, w_r.w), ptx::add2(make_float2(a.z, a.w), make_float2(b.z, b.w))));
       }
-#ifdef HD_EXP_NO_PROD_SILU
 #pragma unroll
-      for (int k = 0; k < 8; ++k) m[k] = pre[k];
-#else
-      // pre[] is t = -log2(e) * (A_i + B_j + r*wr + d*wd): A|B, wr, wd carry the factor (hd_layout.cu)
-      if constexpr (STRICT) {
-        float e[8];
+      for (int k = 0; k < 4; ++k)
+        d[k] = make_float2(ptx::ex2_approx(fminf(q[k].x, 63.0f)), ptx::ex2_approx(fminf(q[k].y, 63.0f)));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(pre[k]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = ptx::rcp_approx(1.0f + e[k]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];            // SiLU / (-ln 2)
-      } else {
-        float hv[8], th[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) hv[k] = -0.34657359027997264f * pre[k];   // v / 2
-#pragma unroll
-        for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(hv[k]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaf(hv[k], th[k], hv[k]);        // SiLU
-      }
-#endif
+      for (int k = 0; k < 4; ++k) d[k] = ptx::add2(d[k], one2);
+      // silu_scaled_pair across the two packed halves of a row: elements (0,2) and (1,3) share a reciprocal
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
-        if (!r.ok[rb]) continue;
-        const float m0 = m[4 * rb], m1 = m[4 * rb + 1], m2 = m[4 * rb + 2], m3 = m[4 * rb + 3];
-        const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
-        uint2 hi;
-        hi.x = *reinterpret_cast<const uint32_t*>(&h01);
-        hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-        uint8_t* dst = stage + 8 * rb * 16;
-        *reinterpret_cast<uint2*>(dst) = hi;
-#ifndef HD_EXP_NO_LO
-        if constexpr (STRICT) {
-          const float l0 = m0 - __uint_as_float(hi.x << 16), l1 = m1 - __uint_as_float(hi.x & 0xffff0000u);
-          const float l2 = m2 - __uint_as_float(hi.y << 16), l3 = m3 - __uint_as_float(hi.y & 0xffff0000u);
-          const __nv_bfloat162 g01 = __floats2bfloat162_rn(l0, l1), g23 = __floats2bfloat162_rn(l2, l3);
-          uint2 lo;
-          lo.x = *reinterpret_cast<const uint32_t*>(&g01);
-          lo.y = *reinterpret_cast<const uint32_t*>(&g23);
-          *reinterpret_cast<uint2*>(dst + A_HALF) = lo;
-        }
+        const float2 pr = ptx::mul2(d[2 * rb], d[2 * rb + 1]);
+        const float2 rc = make_float2(ptx::rcp_approx(pr.x), ptx::rcp_approx(pr.y));
+        const float2 ma = ptx::mul2(q[2 * rb], ptx::mul2(rc, d[2 * rb + 1]));       // SiLU / (-ln 2)
+        const float2 mb = ptx::mul2(q[2 * rb + 1], ptx::mul2(rc, d[2 * rb]));
+        m[4 * rb] = ma.x; m[4 * rb + 1] = ma.y; m[4 * rb + 2] = mb.x; m[4 * rb + 3] = mb.y;
+      }
+    } else
 #endif
+    {
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+      const float4 a = v[rb], b = v[2 + rb];
+      pre[4 * rb + 0] = fmaf(r.dd[rb], w_d.x, fmaf(r.rr[rb], w_r.x, a.x + b.x));
+      pre[4 * rb + 1] = fmaf(r.dd[rb], w_d.y, fmaf(r.rr[rb], w_r.y, a.y + b.y));
+      pre[4 * rb + 2] = fmaf(r.dd[rb], w_d.z, fmaf(r.rr[rb], w_r.z, a.z + b.z));
+      pre[4 * rb + 3] = fmaf(r.dd[rb], w_d.w, fmaf(r.rr[rb], w_r.w, a.w + b.w));
+    }
+#ifdef HD_EXP_NO_PROD_SILU
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = pre[k];
+#else
+    // pre[] is t = -log2(e) * (A_i + B_j + r*wr + d*wd): A|B, wr, wd carry the factor (hd_layout.cu)
+    if constexpr (STRICT) {
+#ifdef HD_EXP_NO_PAIR_RCP
+      float e[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = ptx::ex2_approx(pre[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = ptx::rcp_approx(1.0f + e[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = pre[k] * e[k];            // SiLU / (-ln 2)
+#else
+      // silu_scaled_pair, phase by phase over the 8 elements (4 pairs) so the MUFU latencies overlap
+      float d[8], rc[4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = ptx::ex2_approx(fminf(pre[k], 63.0f));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = 1.0f + d[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rc[k] = ptx::rcp_approx(d[2 * k] * d[2 * k + 1]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        m[2 * k] = pre[2 * k] * (rc[k] * d[2 * k + 1]);            // SiLU / (-ln 2)
+        m[2 * k + 1] = pre[2 * k + 1] * (rc[k] * d[2 * k]);
       }
-    };
-    auto publish = [&](int s) {
-      ptx::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster_relaxed(bar_full(s), 0);
-        else ptx::mbar_arrive_relaxed(bar_full(s));
+#endif
+    } else {
+      float hv[8], th[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hv[k] = -0.34657359027997264f * pre[k];   // v / 2
+#pragma unroll
+      for (int k = 0; k < 8; ++k) th[k] = ptx::tanh_approx(hv[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaf(hv[k], th[k], hv[k]);        // SiLU
+    }
+#endif
+    }
+    (void)pre;
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+      if (!r.ok[rb]) continue;
+      const float m0 = m[4 * rb], m1 = m[4 * rb + 1], m2 = m[4 * rb + 2], m3 = m[4 * rb + 3];
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(m0, m1), h23 = __floats2bfloat162_rn(m2, m3);
+      uint2 hi;
+      hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+      hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+      uint8_t* dst = stage + 8 * rb * 16;
+      *reinterpret_cast<uint2*>(dst) = hi;
+#ifndef HD_EXP_NO_LO
+      if constexpr (STRICT) {
+#ifndef HD_EXP_NO_F32X2
+        const float2 r01 = ptx::add2(make_float2(m0, m1), make_float2(-__uint_as_float(hi.x << 16),
+                                                                      -__uint_as_float(hi.x & 0xffff0000u)));
+        const float2 r23 = ptx::add2(make_float2(m2, m3), make_float2(-__uint_as_float(hi.y << 16),
+                                                                      -__uint_as_float(hi.y & 0xffff0000u)));
+        const float l0 = r01.x, l1 = r01.y, l2 = r23.x, l3 = r23.y;
+#else
+        const float l0 = m0 - __uint_as_float(hi.x << 16), l1 = m1 - __uint_as_float(hi.x & 0xffff0000u);
+        const float l2 = m2 - __uint_as_float(hi.y << 16), l3 = m3 - __uint_as_float(hi.y & 0xffff0000u);
+#endif
+        const __nv_bfloat162 g01 = __floats2bfloat162_rn(l0, l1), g23 = __floats2bfloat162_rn(l2, l3);
+        uint2 lo;
+        lo.x = *reinterpret_cast<const uint32_t*>(&g01);
+        lo.y = *reinterpret_cast<const uint32_t*>(&g23);
+        *reinterpret_cast<uint2*>(dst + A_HALF) = lo;
       }
-    };
-    auto tile_started = [&]() {   // this warp holds the tile's metadata in registers: its slot may be recycled
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tstart);
-    };
-
+#endif
+    }
+  };
+  auto publish = [&](int s) {
+#ifndef HD_EXP_NO_PROXY_FENCE   // timing experiment only
+    ptx::fence_async_smem();
+#endif
+    __syncwarp();
+    if (lane == 0) {
+      if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster_relaxed(bar_full(s), 0);
+      else ptx::mbar_arrive_relaxed(bar_full(s));
+    }
+  };
+  // Operand chunks c_first, c_first + c_step, ... of the tiles [t_begin, t_end).  The producer warps run it once over
+  // all tiles (every chunk, except that they leave the odd chunks of tile 0 to the helpers); HELPER = the epilogue
+  // warps, idle until the first accumulator exists, building the odd chunks of tile 0 - the pipeline fill
+  // (producing the first tile) then takes about half as long.
+  auto produce = [&](int t_begin, int t_end, const bool helper) {
     HD_T0();
     RowState cur, nxt;
     float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1} of the two half stages in flight
 #pragma unroll
     for (int k = 0; k < 4; ++k) va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ntiles > 0) {
-      ptx::mbar_wait(bar_meta, 0);
-      read_meta(0, cur);
+    auto c_first_of = [&](int t) { return (helper && t == 0) ? 1 : 0; };
+    auto c_step_of = [&](int t) { return (FILL_HELP && t == 0) ? 2 : 1; };
+    auto tile_started = [&]() {   // this warp holds the tile's metadata in registers: its slot may be recycled
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(helper ? bar_hmeta : bar_tstart);
+    };
+    if (t_end > t_begin) {
+      if (helper) ptx::mbar_wait(bar_meta0, 0); else ptx::mbar_wait(bar_meta, t_begin & 1);
+      read_meta(t_begin, cur);
       tile_started();
-      load_half(va, cur, 0);
+      load_half(va, cur, c_first_of(t_begin) * HSPS);
     }
     nxt = cur;
     int pending = -1;   // operand stage written but not yet published (published one half step late, when the
                         // fence no longer has to wait for its stores)
-    for (int t = 0; t < ntiles; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
       HD_ACC(0, 0, tid == 0);
+      const int c_step = c_step_of(t);
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = c_first_of(t); c < NCH; c += c_step) {
         const int gc = t * NCH + c, st = gc % NSTAGE;
 #pragma unroll
         for (int pp = 0; pp < HSPS / 2; ++pp) {
           const int hs0 = c * HSPS + 2 * pp;
           load_half(vb, cur, hs0 + 1);
           HD_ACC(0, 5, tid == 0);   // issue loads
+          if (pp == 0 && pending == st) {   // (split first tile) this role's previous chunk sits in the very stage it
+            publish(pending);               // needs next: the MMA can only free it once it has been published
+            pending = -1;
+          }
           if (pp == 0) ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
           HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
           half_step(va, cur, hs0, st);
           HD_ACC(0, 2, tid == 0);   // half steps
           if (pp == 0 && pending >= 0) publish(pending);
           HD_ACC(0, 3, tid == 0);   // publish
-          if (pp + 1 < HSPS / 2 || c + 1 < NCH) {
+          if (pp + 1 < HSPS / 2) {
             load_half(va, cur, hs0 + 2);
-          } else if (t + 1 < ntiles) {   // first operands of the next tile: the tile boundary costs no load latency
+          } else if (c + c_step < NCH) {   // first half step of this role's next chunk
+            load_half(va, cur, (c + c_step) * HSPS);
+          } else if (t + 1 < t_end) {      // first operands of the next tile: the tile boundary costs no load latency
             ptx::mbar_wait(bar_meta, (t + 1) & 1);
             read_meta(t + 1, nxt);
-            load_half(va, nxt, 0);
+            load_half(va, nxt, c_first_of(t + 1) * HSPS);
           }
           HD_ACC(0, 5, tid == 0);
           half_step(vb, cur, hs0 + 1, st);
@@ -415,13 +514,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         }
         pending = st;
       }
-      if (t + 1 < ntiles) {
+      if (t + 1 < t_end) {
         cur = nxt;
         tile_started();
       }
     }
     if (pending >= 0) publish(pending);
     HD_FLUSH(0, tid == 0);
+  };
+
+  if (warp < NPW) {
+    // =========================== producers ===========================
+    produce(0, ntiles, false);
   } else if (warp < MMA_WARP) {
     // =========================== epilogue ===========================
     // warp -> TMEM lane quarter q (= warp % 4) and column half; thread = edge row, 128 of the 256 columns
@@ -432,6 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     float carry = 0.f;
     int cur_recv = -1;
     const float ba = GCL ? p.ba[0] : 0.f;
+    if (FILL_HELP && ntiles > 0) produce(0, 1, true);   // pipeline fill: build the odd operand chunks of tile 0
     auto flush = [&]() {
       if (cur_recv < 0) return;
       if (GCL) p.out[(int64_t)cur_recv * H + etid] = (silu_kout<STRICT>() * carry) / p.norm_div;
@@ -449,6 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       const uint32_t acc = lane_base + 256u * as;
       float v[32];
       float dot = 0.f;
+      float2 dot2 = make_float2(0.f, 0.f);   // packed partial sums of the attention / coordinate dot product
 #pragma unroll 1
       for (int cc = 0; cc < (warp_live ? 4 : 0); ++cc) {
         ptx::tmem_ld32(acc + 32 * cc, v);
@@ -462,10 +568,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 #else
           // bb = -log2(e) * b2; KACC undoes the producer's output scale: t2 = -log2(e) * (W2 . SiLU + b2)
           constexpr float KACC = silu_kacc<STRICT>();
-          const float m0 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 0], bb.x));
-          const float m1 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 1], bb.y));
-          const float m2 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 2], bb.z));
-          const float m3 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 3], bb.w));
+          float m0, m1, m2, m3;
+#if !defined(HD_EXP_NO_F32X2) && !defined(HD_EXP_NO_PAIR_RCP)
+          if constexpr (STRICT) {
+            // packed fp32x2 (FADD2 / FMUL2 / FFMA2); KACC == 1 in strict mode.  Elements (0,2) and (1,3) share a
+            // reciprocal (silu_scaled_pair across the two packed halves)
+            const float2 ta = ptx::add2(make_float2(v[4 * k4 + 0], v[4 * k4 + 1]), make_float2(bb.x, bb.y));
+            const float2 tb = ptx::add2(make_float2(v[4 * k4 + 2], v[4 * k4 + 3]), make_float2(bb.z, bb.w));
+            const float2 one2 = make_float2(1.0f, 1.0f);
+            const float2 da = ptx::add2(make_float2(ptx::ex2_approx(fminf(ta.x, 63.0f)), ptx::ex2_approx(fminf(ta.y, 63.0f))), one2);
+            const float2 db = ptx::add2(make_float2(ptx::ex2_approx(fminf(tb.x, 63.0f)), ptx::ex2_approx(fminf(tb.y, 63.0f))), one2);
+            const float2 pr = ptx::mul2(da, db);
+            const float2 rc = make_float2(ptx::rcp_approx(pr.x), ptx::rcp_approx(pr.y));
+            const float2 ma = ptx::mul2(ta, ptx::mul2(rc, db));
+            const float2 mb = ptx::mul2(tb, ptx::mul2(rc, da));
+            dot2 = ptx::fma2(ma, make_float2(ww.x, ww.y), dot2);
+            dot2 = ptx::fma2(mb, make_float2(ww.z, ww.w), dot2);
+            v[4 * k4 + 0] = ma.x; v[4 * k4 + 1] = ma.y; v[4 * k4 + 2] = mb.x; v[4 * k4 + 3] = mb.y;
+            continue;
+          }
+#endif
+#ifndef HD_EXP_NO_PAIR_RCP
+          if constexpr (STRICT) {
+            silu_scaled_pair(fmaf(KACC, v[4 * k4 + 0], bb.x), fmaf(KACC, v[4 * k4 + 1], bb.y), m0, m1);
+            silu_scaled_pair(fmaf(KACC, v[4 * k4 + 2], bb.z), fmaf(KACC, v[4 * k4 + 3], bb.w), m2, m3);
+          } else
+#endif
+          {
+            m0 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 0], bb.x));
+            m1 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 1], bb.y));
+            m2 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 2], bb.z));
+            m3 = silu_scaled<STRICT>(fmaf(KACC, v[4 * k4 + 3], bb.w));
+          }
 #endif
           dot = fmaf(m0, ww.x, dot);
           dot = fmaf(m1, ww.y, dot);
@@ -477,6 +611,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       }
       HD_ACC(1, 1, etid == 0);   // pass 1
       // full-row dot product: exchange the two column halves
+      dot += dot2.x + dot2.y;
       s_dot[half * TILE_M + 32 * q + lane] = dot;
       ptx::named_bar_sync(4, EPI_THREADS);
       HD_ACC(1, 2, etid == 0);   // exchange barrier
@@ -497,6 +632,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
           ptx::tmem_ld32(acc + 32 * cc, v);
           ptx::tmem_wait_ld();
           float f[16], g[8], hsum[4];
+#ifndef HD_EXP_NO_F32X2
+          // the same transpose-reduction with the multiplies and adds packed two by two (FMUL2 / FADD2)
+          const float2 scale2 = make_float2(scale, scale);
+          const bool up4 = (lane & 4) != 0, up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) {
+            const float2 lo_v = ptx::mul2(make_float2(v[k], v[k + 1]), scale2);
+            const float2 hi_v = ptx::mul2(make_float2(v[k + 16], v[k + 17]), scale2);
+            const float2 send = up4 ? lo_v : hi_v, keep = up4 ? hi_v : lo_v;
+            const float2 got = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 4), __shfl_xor_sync(0xffffffffu, send.y, 4));
+            const float2 sum = ptx::add2(keep, got);
+            f[k] = sum.x; f[k + 1] = sum.y;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            const float2 a = make_float2(f[k], f[k + 1]), b = make_float2(f[k + 8], f[k + 9]);
+            const float2 send = up2 ? a : b, keep = up2 ? b : a;
+            const float2 got = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 2), __shfl_xor_sync(0xffffffffu, send.y, 2));
+            const float2 sum = ptx::add2(keep, got);
+            g[k] = sum.x; g[k + 1] = sum.y;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k += 2) {
+            const float2 a = make_float2(g[k], g[k + 1]), b = make_float2(g[k + 4], g[k + 5]);
+            const float2 send = up1 ? a : b, keep = up1 ? b : a;
+            const float2 got = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 1), __shfl_xor_sync(0xffffffffu, send.y, 1));
+            const float2 sum = ptx::add2(keep, got);
+            hsum[k] = sum.x; hsum[k + 1] = sum.y;
+          }
+#else
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const float lo_v = v[k] * scale, hi_v = v[k + 16] * scale;
@@ -516,6 +681,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
             const float keep = (lane & 1) ? g[k + 4] : g[k];
             hsum[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
           }
+#endif
           float4 o;
           o.x = hsum[0]; o.y = hsum[1]; o.z = hsum[2]; o.w = hsum[3];
           *reinterpret_cast<float4*>(s_scr + (4 * q + (lane >> 3)) * H + 128 * half + 32 * cc + c4 + c2 + c1) = o;
@@ -582,6 +748,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     int win_b0 = -1, win_first = 0, win_n = 0, win_node0 = 0;
     for (int t = 0; t < ntiles; ++t) {
       if (t > 0) ptx::mbar_wait(bar_tstart, (t - 1) & 1);   // producers hold tile t-1's metadata in registers
+      if (FILL_HELP && t == PMETA_BUFS) ptx::mbar_wait(bar_hmeta, 0);   // ... and so do the helpers of tile 0 (its slot is recycled now)
       if (big_b && row_begin + t * TILE_M < row_end) {
         if (win_b0 < 0) win_b0 = find_mol_warp(p.row_off, p.B, row_begin, lane);
         const int wb = min(win_b0 + lane, p.B - 1);
@@ -657,7 +824,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         if ((row & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (row >> 3)] = make_int2(m.recv, e.flags != 0);
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_meta);
+      if (lane == 0) {
+        ptx::mbar_arrive(bar_meta);
+        if (FILL_HELP && t == 0) ptx::mbar_arrive(bar_meta0);
+      }
     }
   } else {
     // =========================== MMA issuer ===========================
@@ -691,7 +861,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
                 const uint64_t db_hi = ptx::smem_desc(sbase + S::OFF_W + kgw, W_KG, 128);
                 ptx::mma_bf16<2>(d, da_hi, db_hi, IDESC, acc_on);
                 if constexpr (STRICT) {
-                  const uint64_t db_lo = ptx::smem_desc(sbase + S::OFF_W + W_HALF + kgw, W_KG, 128);
+                  const uint64_t db_lo = ptx::smem_desc(sbase + S::OFF_W + (S::W_PARTS - 1) * W_HALF + kgw, W_KG, 128);
                   ptx::mma_bf16<2>(d, da_hi, db_lo, IDESC, 1u);
                   ptx::mma_bf16<2>(d, da_lo, db_hi, IDESC, 1u);
                 }
@@ -699,11 +869,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                   const uint32_t d = tmem + 256u * as + 128u * hf;
-                  const uint32_t wb = sbase + S::OFF_W + hf * (STRICT ? 2 : 1) * W_HALF;
+                  const uint32_t wb = sbase + S::OFF_W + hf * S::W_PARTS * W_HALF;
                   const uint64_t db_hi = ptx::smem_desc(wb + kgw, W_KG, 128);
                   ptx::mma_bf16<1>(d, da_hi, db_hi, IDESC, acc_on);
                   if constexpr (STRICT) {
-                    const uint64_t db_lo = ptx::smem_desc(wb + W_HALF + kgw, W_KG, 128);
+                    const uint64_t db_lo = ptx::smem_desc(wb + (S::W_PARTS - 1) * W_HALF + kgw, W_KG, 128);
                     ptx::mma_bf16<1>(d, da_hi, db_lo, IDESC, 1u);
                     ptx::mma_bf16<1>(d, da_lo, db_hi, IDESC, 1u);
                   }
@@ -758,6 +928,9 @@ static int launch_edge(const Params& p, cudaStream_t st) {
   auto kern = edge_tc_k<GCL, STRICT, CG, WIDE>;
   if (!configured) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+#ifdef HD_EXP_CARVEOUT
+    HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, HD_EXP_CARVEOUT));
+#endif
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
