@@ -534,15 +534,17 @@ def reverse_step_roofline(loop):
     L = native.lib()
     B, N, F = loop.B, loop.N, loop.F
     st = native.stream_ptr()
-    zs = torch.empty_like(loop.z)
+    zs, eps = torch.empty_like(loop.z), torch.randn_like(loop.z)
+    sched = loop.table.sched[0].contiguous()
     ms = _time_launches(lambda: native.check(L.hd_reverse_step(
-        native.ptr(loop.z), native.ptr(loop.eps), native.ptr(loop.rx), native.ptr(loop.rh), native.ptr(loop.sizes), B,
-        N, F, native.ptr(loop.sched_cur), 1, native.ptr(zs), None, st), "hd_reverse_step"))
+        native.ptr(loop.z), native.ptr(eps), native.ptr(loop.rx), native.ptr(loop.rh), native.ptr(loop.sizes), B,
+        N, F, native.ptr(sched), 1, native.ptr(zs), None, st), "hd_reverse_step"))
     peaks, src = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     nbytes = 4.0 * (3 + F) * N * B * 4
     achieved = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "diffusion update hd::reverse_step_k (timed alone, back to back)", "bound": "hbm",
+    return {"kernel": "diffusion update hd::reverse_step_k (timed alone, back to back; in the loop it is part of "
+                      "sampler_tail_k)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": f"copy bandwidth, {src}", "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
             "note": "176*N bytes per molecule: at B*N = %d nodes the launch moves %.0f KB, so it is launch-latency "

@@ -180,11 +180,22 @@ __global__ void __launch_bounds__(256) out_vel_k(const float* __restrict__ h, co
                                                  const int32_t* __restrict__ sizes, int N,
                                                  const float* __restrict__ xf, const float* __restrict__ x0,
                                                  float* __restrict__ eps_raw, int32_t* __restrict__ nanflag,
-                                                 const int32_t* __restrict__ node_off) {
+                                                 const int32_t* __restrict__ node_off, int32_t* __restrict__ state) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_out[64];
   const int64_t r = blockIdx.x;
+  if (state) {
+    // sampling loop: this forward belongs to step k = state[0] (no CTA of this kernel writes it); its NaN flag is
+    // state[2 + (k & 1)].  Block 0 latches k for the tail kernel and clears the flag of step k+1 - last read by the
+    // tail of step k-1, which has completed.
+    const int k = state[0];
+    nanflag = state + 2 + (k & 1);
+    if (r == 0 && threadIdx.x == 0) {
+      state[1] = k;
+      state[2 + ((k + 1) & 1)] = 0;
+    }
+  }
   const int tid = threadIdx.x, b = (int)(r / N), i = (int)(r % N), warp = tid >> 5, lane = tid & 31;
   const bool real = i < sizes[b];
   const int64_t o = node_off ? (real ? node_off[b] + i : 0) : r;   // row of h / xf / x0 (ragged: real nodes only)
@@ -400,6 +411,248 @@ __global__ void __launch_bounds__(128) final_decode_k(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The sampling loop's own kernels (hd_sampler_begin / _step / _final): everything between two EGNN stacks of
+// DiffusionQM9.sample (diffusion_qm9.py:375-384) in ONE launch - the centre-of-gravity projection and NaN guard that end
+// _forward (en_dynamics.py:109-116), the reverse update (diffusion_qm9.py:328-345), the step counter, and the input side
+// of the next forward (en_dynamics.py:56-79 masking / time / context channels, egnn_new.py:197 embedding) together with
+// the first sub-layer's A|B pre-projection folded through the embedding (hd_layout.cu fuse_embed_k).
+// ---------------------------------------------------------------------------------------
+struct SamplerArgs {
+  // chain state
+  float* z;                  // [B,N,3+F], updated in place
+  const float* rx;           // [B,N,3]   raw randn draw of this step
+  const float* rh;           // [B,N,F]
+  const float* t_table;      // [T+1]
+  const float* sched_table;  // [T+1][sched_rows][3]
+  const float* context;      // [B,N,C] or null
+  const int32_t* sizes;
+  int32_t* state;            // Workspace::state
+  int32_t* flags;
+  const float* eps_raw;      // [B,N,3+F] written by out_vel_k
+  int B, N, F, C, T, sched_rows, ragged;
+  // input side of the next forward
+  const float *emb_wT, *emb_b, *emb_abT, *emb_abb;   // emb_abT null: no A|B image (fp32 engine)
+  float *x, *x0, *x2, *h, *ab;
+  int32_t *row_off, *node_off;                       // prefix tables (written by the begin kernel, read afterwards)
+  int rows_bound;
+  // final decode
+  float norm_x, norm_h, bias_h;
+  float *x_out, *h_out;
+};
+
+// Input side of an EGNN forward for molecule b from its z rows in shared memory (zv [N][D]): x, x0 (masked), the
+// embedding h and, for the tensor-core engines, the first sub-layer's A|B operands.  row0 = first workspace row of the
+// molecule.  Called by all 256 threads of the block; thread = channel.  The thread keeps its columns of the (folded)
+// embedding weights in registers and walks over the nodes without any barrier.
+__device__ __forceinline__ void embed_molecule(const SamplerArgs& p, const float* zv, int b, int n, int64_t row0,
+                                               float t) {
+  constexpr int FMAX = 12;                  // input channels held in registers (F + time + context); more: re-read
+  const int N = p.N, F = p.F, C = p.C, D = 3 + F, Fi = F + 1 + C, tid = threadIdx.x;
+  const int64_t rows = (int64_t)p.B * N;
+  const int count = p.ragged ? n : N;      // ragged node rows: padded nodes own no row
+  const bool ab = p.emb_abT != nullptr;
+  for (int idx = tid; idx < count * 3; idx += 256) {
+    const int i = idx / 3, ch = idx - 3 * i;
+    const float v = i < n ? zv[i * D + ch] : 0.f;
+    p.x[(row0 + i) * 3 + ch] = v;
+    p.x0[(row0 + i) * 3 + ch] = v;
+  }
+  float w[FMAX], wa[FMAX], wb[FMAX];
+#pragma unroll
+  for (int f = 0; f < FMAX; ++f) {
+    w[f] = f < Fi ? p.emb_wT[f * H + tid] : 0.f;
+    wa[f] = ab && f < Fi ? p.emb_abT[f * 2 * H + tid] : 0.f;
+    wb[f] = ab && f < Fi ? p.emb_abT[f * 2 * H + H + tid] : 0.f;
+  }
+  const float bias = p.emb_b[tid], bias_a = ab ? p.emb_abb[tid] : 0.f, bias_b = ab ? p.emb_abb[H + tid] : 0.f;
+  for (int i = 0; i < count; ++i) {
+    const int64_t o = row0 + i;
+    float v = 0.f, a0 = 0.f, a1 = 0.f;
+    if (i < n) {
+      v = bias;
+      a0 = bias_a;
+      a1 = bias_b;
+      const float* zi = zv + i * D + 3;     // the F feature channels (shared memory, broadcast reads)
+      const float* ci = p.context + ((int64_t)b * N + i) * C;
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) {
+        if (f < Fi) {
+          // time and context are not masked (en_dynamics.py:66-79)
+          const float in = f < F ? zi[f] : (f == F ? t : ci[f - F - 1]);
+          v = fmaf(in, w[f], v);
+          a0 = fmaf(in, wa[f], a0);
+          a1 = fmaf(in, wb[f], a1);
+        }
+      }
+      for (int f = FMAX; f < Fi; ++f) {    // wider inputs than the register file holds: weights re-read per node
+        const float in = f < F ? zi[f] : (f == F ? t : ci[f - F - 1]);
+        v = fmaf(in, __ldg(p.emb_wT + f * H + tid), v);
+        if (ab) {
+          a0 = fmaf(in, __ldg(p.emb_abT + f * 2 * H + tid), a0);
+          a1 = fmaf(in, __ldg(p.emb_abT + f * 2 * H + H + tid), a1);
+        }
+      }
+    }
+    p.h[o * H + tid] = v;
+    if (ab) {   // K-chunk-major operand image of the edge kernel: [col / 16][row][col % 16], A then B
+      p.ab[((int64_t)(tid >> 4) * rows + o) * 16 + (tid & 15)] = a0;
+      p.ab[((int64_t)((H + tid) >> 4) * rows + o) * 16 + (tid & 15)] = a1;
+    }
+  }
+}
+
+// First kernel of a chain: loop state, the prefix tables of the edge kernel / ragged layout, and the input side of the
+// first forward.  One CTA per molecule, 256 threads.
+__global__ void __launch_bounds__(256) sampler_begin_k(const SamplerArgs p) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sm[];   // zv [N*D]
+  __shared__ int s_part[8];
+  const int D = 3 + p.F, b = blockIdx.x, tid = threadIdx.x, n = p.sizes[b];
+  if (b == 0 && tid < 32) {
+    if (tid < 4) p.state[tid] = 0;
+    int carry_r = 0, carry_n = 0;
+    if (tid == 0) {
+      if (p.row_off) p.row_off[0] = 0;
+      if (p.node_off) p.node_off[0] = 0;
+    }
+    for (int base = 0; base < p.B; base += 32) {
+      const int bb = base + tid;
+      const int nn = bb < p.B ? p.sizes[bb] : 0;
+      int vr = nn * ((nn + 7) & ~7), vn = nn;
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int ur = __shfl_up_sync(0xffffffffu, vr, o2), un = __shfl_up_sync(0xffffffffu, vn, o2);
+        if (tid >= o2) {
+          vr += ur;
+          vn += un;
+        }
+      }
+      if (bb < p.B) {
+        if (p.row_off) p.row_off[bb + 1] = carry_r + vr;
+        if (p.node_off) p.node_off[bb + 1] = carry_n + vn;
+      }
+      carry_r += __shfl_sync(0xffffffffu, vr, 31);
+      carry_n += __shfl_sync(0xffffffffu, vn, 31);
+    }
+    // the caller's bound on sum(sizes) sized the node-GEMM grids: rows beyond it would silently go missing
+    if (tid == 0 && p.ragged && carry_n > p.rows_bound && p.flags) atomicOr(p.flags, HD_FLAG_MASK);
+  }
+  // first workspace row of this molecule: every CTA sums the sizes ahead of it itself (the table block 0 publishes is
+  // for the kernels that follow)
+  int64_t row0 = (int64_t)b * p.N;
+  if (p.ragged) {
+    int part = 0;
+    for (int k = tid; k < b; k += 256) part += p.sizes[k];
+    part = warp_sum_int(part);
+    if ((tid & 31) == 0) s_part[tid >> 5] = part;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base += s_part[w];
+    row0 = base;
+  }
+  const float* zsrc = p.z + (int64_t)b * p.N * D;
+  for (int idx = tid; idx < p.N * D; idx += 256) sm[idx] = zsrc[idx];
+  // x2, the ping-pong partner of the coordinate updates: padded rows must be 0 and are never written afterwards
+  for (int idx = tid; idx < (p.ragged ? n : p.N) * 3; idx += 256) p.x2[row0 * 3 + idx] = 0.f;
+  __syncthreads();
+  embed_molecule(p, sm, b, n, row0, p.t_table[0]);
+}
+
+// Between two forwards (FINAL: after the last one).  One CTA per molecule, 256 threads.
+template <bool FINAL>
+__global__ void __launch_bounds__(256) sampler_tail_k(const SamplerArgs p) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sm[];  // nz [N*D], ev [N*D], zv [N*D]
+  __shared__ float s_mean[3];
+  __shared__ float s_chk[3];
+  const int N = p.N, F = p.F, D = 3 + F, b = blockIdx.x, tid = threadIdx.x, n = p.sizes[b];
+  float* nz = sm;
+  float* ev = sm + N * D;
+  float* zv = ev + N * D;
+  const int k = min(p.state[1], p.T);          // the step whose forward has just run (latched by out_vel_k)
+  const bool nan = p.state[2 + (k & 1)] != 0;  // NaN guard of that forward (whole batch, en_dynamics.py:109-111)
+  const float* sc = p.sched_table + ((int64_t)k * p.sched_rows + (p.sched_rows > 1 ? b : 0)) * 3;
+  const float c0 = sc[0], c1 = sc[1], c2 = sc[2];
+  const float* zsrc = p.z + (int64_t)b * N * D;
+  const float* esrc = p.eps_raw + (int64_t)b * N * D;
+  if (tid < 3) s_chk[tid] = 0.f;
+  load_noise(p.rx + (int64_t)b * N * 3, p.rh + (int64_t)b * N * F, N, F, n, nz, s_mean);
+  float pad_abs = 0.f, max_abs = 0.f;
+  for (int idx = tid; idx < N * D; idx += 256) {
+    const float v = zsrc[idx];
+    zv[idx] = v;
+    float e = esrc[idx];
+    if (nan && idx % D < 3) e = 0.f;
+    ev[idx] = e;
+    if (idx % D < 3) {
+      if (idx / D >= n) pad_abs = fmaxf(pad_abs, fabsf(v));
+      max_abs = fmaxf(max_abs, fabsf(v));
+    }
+  }
+  if (nan && p.flags && b == 0 && tid == 0) atomicOr(p.flags, HD_FLAG_NAN);
+  __syncthreads();
+  float mean[3];
+  block_mean3(ev, N, D, n, s_mean, mean);      // remove_mean_with_mask that ends _forward (en_dynamics.py:116)
+  for (int idx = tid; idx < N * 3; idx += 256) {
+    const int i = idx / 3, ch = idx % 3;
+    if (i < n) ev[i * D + ch] -= mean[ch];
+  }
+  __syncthreads();
+  if (FINAL) {
+    // sample_p_xh_given_z0 (diffusion_qm9.py:294-310, :174-179): {alpha_0, sigma_0, sigma_x} = c0, c1, c2
+    for (int idx = tid; idx < N * D; idx += 256) {
+      const int i = idx / D, ch = idx % D;
+      if (ch < 3) {
+        const float mu = 1.0f / c0 * (zv[idx] - c1 * ev[idx]);   // :244
+        p.x_out[((int64_t)b * N + i) * 3 + ch] = (mu + c2 * nz[idx]) * p.norm_x;
+      } else {
+        p.h_out[((int64_t)b * N + i) * F + (ch - 3)] = (zv[idx] * p.norm_h + p.bias_h) * (i < n ? 1.f : 0.f);
+      }
+    }
+    return;
+  }
+  // sample_p_zs_given_zt after the network call (diffusion_qm9.py:328-345): {alpha_t|s, sigma2_t|s/alpha_t|s/sigma_t,
+  // sigma_t|s sigma_s / sigma_t} = c0, c1, c2.  assert_mean_zero_with_mask(zt_x) (models/utils.py:65-75) per molecule:
+  atomicMax(reinterpret_cast<int*>(&s_chk[0]), __float_as_int(pad_abs));   // float max of non-negatives == int max
+  atomicMax(reinterpret_cast<int*>(&s_chk[1]), __float_as_int(max_abs));
+  __syncthreads();
+  float zsum[3];
+  block_mean3(zv, N, D, 1, s_mean, zsum);      // n = 1 -> plain sums
+  if (p.flags && tid == 0) {
+    const float err = fmaxf(fabsf(zsum[0]), fmaxf(fabsf(zsum[1]), fabsf(zsum[2])));
+    int f = 0;
+    if (!(s_chk[0] < 1e-4f)) f |= HD_FLAG_MASK;
+    if (!(err / (s_chk[1] + 1e-10f) < 1e-2f)) f |= HD_FLAG_COG;
+    if (f) atomicOr(p.flags, f);
+  }
+  block_mean3(ev, N, D, n, s_mean, mean);      // :330 second CoG removal on eps_x
+  for (int idx = tid; idx < N * D; idx += 256) {
+    const int i = idx / D, ch = idx % D;
+    float e = ev[idx];
+    if (ch < 3 && i < n) e -= mean[ch];
+    const float mu = zv[idx] / c0 - c1 * e;    // :331
+    zv[idx] = mu + c2 * nz[idx];               // :337, :442
+  }
+  __syncthreads();
+  block_mean3(zv, N, D, n, s_mean, mean);      // :340-344
+  float* dst = p.z + (int64_t)b * N * D;
+  for (int idx = tid; idx < N * D; idx += 256) {
+    const int i = idx / D, ch = idx % D;
+    float v = zv[idx];
+    if (ch < 3 && i < n) v -= mean[ch];
+    zv[idx] = v;
+    dst[idx] = v;
+  }
+  if (b == 0 && tid == 0) p.state[0] = k + 1;  // read by the next forward's out_vel_k only
+  __syncthreads();
+  const int64_t row0 = p.ragged ? p.node_off[b] : (int64_t)b * N;
+  embed_molecule(p, zv, b, n, row0, p.t_table[min(k + 1, p.T)]);
+}
+
 __device__ __forceinline__ float softplus_t(float v) { return v > 20.0f ? v : log1pf(expf(v)); }  // F.softplus
 __device__ __forceinline__ float logsigmoid_t(float v) { return fminf(v, 0.0f) - log1pf(expf(-fabsf(v))); }
 __device__ __forceinline__ float sigmoid_t(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -468,14 +721,14 @@ static int sub_equiv(const FwdCtx& c, int si, const float* h, const float* x, co
 }
 
 // EGNN blocks (egnn_new.py:198-199, :139-152) on ws.h / ws.x; returns the buffers holding the final h and x
-static int run_blocks(const FwdCtx& c, int engine, float** h_final, float** x_final) {
+static int run_blocks(const FwdCtx& c, int engine, float** h_final, float** x_final, bool ab_ready = false) {
   float* h = reinterpret_cast<float*>(c.ws + c.W.h);
   float* h2 = reinterpret_cast<float*>(c.ws + c.W.h2);
   float* x = reinterpret_cast<float*>(c.ws + c.W.x);
   float* x2 = reinterpret_cast<float*>(c.ws + c.W.x2);
   const float* x0 = reinterpret_cast<const float*>(c.ws + c.W.x0);
   int si = 0, rc;
-  c.ab_ready = false;
+  c.ab_ready = ab_ready;   // the sampling loop's tail kernel has already produced block 0's A|B operands
   for (int l = 0; l < c.cfg->n_layers; ++l) {
     for (int s = 0; s < c.cfg->inv_sublayers; ++s) {
       if (engine != HD_ENGINE_FP32 && c.L->subs[si].fuse_next) {
@@ -609,7 +862,7 @@ HD_API int32_t hd_dynamics_forward_ragged(const hd_config* cfg, const void* pack
   if ((rc = run_blocks(c, engine, &hf, &xf))) return rc;
   HD_CHECK_CUDA(launch_pdl(out_vel_k, dim3((unsigned)BN), dim3(256), 0, c.stream, (const float*)hf, PF(L.out_w),
                           PF(L.out_b), Fi, F, sizes, N, (const float*)xf, (const float*)WF(c.W.x0), WF(c.W.eps_raw),
-                          nanflag, (const int32_t*)node_off));
+                          nanflag, (const int32_t*)node_off, (int32_t*)nullptr));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(cog_k, dim3(B), dim3(128), sizeof(float) * N * D, c.stream, (const float*)WF(c.W.eps_raw),
                           sizes, N, F, (const int32_t*)nanflag, eps, flags));
@@ -697,6 +950,99 @@ HD_API int32_t hd_edge_kernel_only(const hd_config* cfg, const void* packed, int
   return tc_edge_only(c, si, x, x0, engine);
 }
 
+// ---- the sampling loop (hd_sampler_begin / _step / _final) -------------------------------------------------------
+struct SamplerCall {
+  Layout L;
+  FwdCtx c;
+  SamplerArgs a;
+  int engine;
+  size_t tail_smem;
+};
+
+static int sampler_setup(SamplerCall* sc, const hd_config* cfg, const void* packed, float* z, const float* t_table,
+                         const float* sched_table, int sched_rows, int T, const float* context, int context_nf,
+                         const int32_t* sizes, int B, int N, int live_rows, void* workspace, int32_t* flags, int engine,
+                         hd_stream_t stream) {
+  if (live_rows < 0 || (int64_t)live_rows > (int64_t)B * N) {
+    set_error("live_rows=%d outside [0, B*N]", live_rows);
+    return HD_E_INVALID;
+  }
+  if (live_rows > 0) engine |= HD_ENGINE_RAGGED_ROWS;
+  const bool ragged_req = (engine & HD_ENGINE_RAGGED_ROWS) != 0;
+  engine &= ~HD_ENGINE_RAGGED_ROWS;
+  int rc = check_common(cfg, packed, sizes, B, N, engine);
+  if (rc) return rc;
+  if (!z || !t_table || !workspace || T < 1 || (sched_table && sched_rows != 1 && sched_rows != B)) {
+    set_error("bad argument (null pointer, T=%d, sched_rows=%d)", T, sched_rows);
+    return HD_E_INVALID;
+  }
+  if (context_nf < 0 || (context_nf > 0 && !context) || cfg->in_node_nf - 1 - context_nf < 0) {
+    set_error("bad context (context_nf=%d, in_node_nf=%d)", context_nf, cfg->in_node_nf);
+    return HD_E_INVALID;
+  }
+  if (!make_layout(*cfg, &sc->L)) return HD_E_INVALID;
+  const int Fi = cfg->in_node_nf, C = context_nf, F = Fi - 1 - C, D = 3 + F;
+  if (Fi > 64 || D > 256) {
+    set_error("in_node_nf=%d too large for the fused input kernel", Fi);
+    return HD_E_INVALID;
+  }
+  const bool tc = engine != HD_ENGINE_FP32;
+  if (tc && B > 4096) {
+    set_error("tensor-core engine supports at most 4096 molecules per call (got %d)", B);
+    return HD_E_INVALID;
+  }
+  sc->engine = engine;
+  sc->c = FwdCtx{cfg, &sc->L, static_cast<const char*>(packed), static_cast<char*>(workspace),
+                 make_workspace(*cfg, B, N), sizes, B, N, static_cast<cudaStream_t>(stream)};
+  FwdCtx& c = sc->c;
+  auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
+  auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  const bool ragged = tc && ragged_req;
+  c.x_prezeroed = true;
+  c.planned = tc;
+  c.node_off = ragged ? reinterpret_cast<int32_t*>(c.ws + c.W.node_off) : nullptr;
+  c.rows_bound = ragged && live_rows > 0 ? live_rows : 0;
+  SamplerArgs& a = sc->a;
+  a = SamplerArgs{};
+  a.z = z;
+  a.t_table = t_table;
+  a.sched_table = sched_table;
+  a.context = context;
+  a.sizes = sizes;
+  a.state = reinterpret_cast<int32_t*>(c.ws + c.W.state);
+  a.flags = flags;
+  a.eps_raw = WF(c.W.eps_raw);
+  a.B = B; a.N = N; a.F = F; a.C = C; a.T = T; a.sched_rows = sched_rows; a.ragged = ragged ? 1 : 0;
+  a.emb_wT = PF(sc->L.emb_wT);
+  a.emb_b = PF(sc->L.emb_b);
+  a.emb_abT = tc ? PF(sc->L.emb_abT) : nullptr;
+  a.emb_abb = tc ? PF(sc->L.emb_abb) : nullptr;
+  a.x = WF(c.W.x); a.x0 = WF(c.W.x0); a.x2 = WF(c.W.x2); a.h = WF(c.W.h); a.ab = WF(c.W.ab);
+  a.row_off = tc ? reinterpret_cast<int32_t*>(c.ws + c.W.row_off) : nullptr;
+  a.node_off = const_cast<int32_t*>(c.node_off);
+  a.rows_bound = live_rows > 0 ? live_rows : B * N;
+  sc->tail_smem = sizeof(float) * 3 * N * D;
+  return HD_OK;
+}
+
+// EGNN blocks + output head of the forward whose input side the previous begin / tail kernel prepared
+static int sampler_forward(SamplerCall* sc) {
+  FwdCtx& c = sc->c;
+  const hd_config* cfg = c.cfg;
+  const int Fi = cfg->in_node_nf;
+  auto WF = [&](int64_t off) { return reinterpret_cast<float*>(c.ws + off); };
+  auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
+  float *hf = nullptr, *xf = nullptr;
+  int rc = run_blocks(c, sc->engine, &hf, &xf, sc->engine != HD_ENGINE_FP32);
+  if (rc) return rc;
+  HD_CHECK_CUDA(launch_pdl(out_vel_k, dim3((unsigned)((int64_t)c.B * c.N)), dim3(256), 0, c.stream, (const float*)hf,
+                          PF(sc->L.out_w), PF(sc->L.out_b), Fi, sc->a.F, c.sizes, c.N, (const float*)xf,
+                          (const float*)WF(c.W.x0), WF(c.W.eps_raw), (int32_t*)nullptr, (const int32_t*)c.node_off,
+                          sc->a.state));
+  count_launch();
+  return HD_OK;
+}
+
 static int check_mol(const int32_t* sizes, int B, int N, int F) {
   if (!sizes || B < 1 || N < 1 || N > 1024 || F < 0 || F > 64) {
     set_error("bad shape B=%d N=%d F=%d", B, N, F);
@@ -766,6 +1112,74 @@ HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* 
   final_decode_k<<<B, 128, sizeof(float) * N * (3 + F), static_cast<cudaStream_t>(stream)>>>(
       z0, eps0, randn_x, randn_h, sizes, N, F, sched, sched_per_mol, norm_x, norm_h, bias_h, x, h);
   HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+HD_API int32_t hd_sampler_begin(const hd_config* cfg, const void* packed, const float* z, const float* t_table, int32_t T,
+                                const float* context, int32_t context_nf, const int32_t* sizes, int32_t B, int32_t N,
+                                int32_t live_rows, void* workspace, int32_t* flags, int32_t engine, hd_stream_t stream) {
+  SamplerCall sc;
+  int rc = sampler_setup(&sc, cfg, packed, const_cast<float*>(z), t_table, nullptr, 1, T, context, context_nf, sizes, B, N,
+                         live_rows, workspace, flags, engine, stream);
+  if (rc) return rc;
+  HD_CHECK_CUDA(launch_pdl(sampler_begin_k, dim3(B), dim3(256), sizeof(float) * N * (3 + sc.a.F), sc.c.stream, sc.a));
+  count_launch();
+  return HD_OK;
+}
+
+HD_API int32_t hd_sampler_step(const hd_config* cfg, const void* packed, float* z, const float* randn_x,
+                               const float* randn_h, const float* t_table, const float* sched_table, int32_t sched_rows,
+                               int32_t T, const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
+                               int32_t N, int32_t live_rows, void* workspace, int32_t* flags, int32_t engine,
+                               hd_stream_t stream) {
+  SamplerCall sc;
+  if (!randn_x || !randn_h || !sched_table) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  int rc = sampler_setup(&sc, cfg, packed, z, t_table, sched_table, sched_rows, T, context, context_nf, sizes, B, N,
+                         live_rows, workspace, flags, engine, stream);
+  if (rc) return rc;
+  if ((rc = sampler_forward(&sc))) return rc;
+  sc.a.rx = randn_x;
+  sc.a.rh = randn_h;
+  if (sc.tail_smem > 48 * 1024) {
+    set_error("N=%d too large for the fused tail kernel", N);
+    return HD_E_INVALID;
+  }
+  HD_CHECK_CUDA(launch_pdl(sampler_tail_k<false>, dim3(B), dim3(256), sc.tail_smem, sc.c.stream, sc.a));
+  count_launch();
+  return HD_OK;
+}
+
+HD_API int32_t hd_sampler_final(const hd_config* cfg, const void* packed, const float* z, const float* randn_x,
+                                const float* randn_h, const float* t_table, const float* sched_table,
+                                int32_t sched_rows, int32_t T, const float* context, int32_t context_nf,
+                                const int32_t* sizes, int32_t B, int32_t N, int32_t live_rows, float norm_x,
+                                float norm_h, float bias_h, float* x, float* h, void* workspace, int32_t* flags,
+                                int32_t engine, hd_stream_t stream) {
+  SamplerCall sc;
+  if (!randn_x || !randn_h || !sched_table || !x || !h) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  int rc = sampler_setup(&sc, cfg, packed, const_cast<float*>(z), t_table, sched_table, sched_rows, T, context, context_nf,
+                         sizes, B, N, live_rows, workspace, flags, engine, stream);
+  if (rc) return rc;
+  if ((rc = sampler_forward(&sc))) return rc;
+  sc.a.rx = randn_x;
+  sc.a.rh = randn_h;
+  sc.a.norm_x = norm_x;
+  sc.a.norm_h = norm_h;
+  sc.a.bias_h = bias_h;
+  sc.a.x_out = x;
+  sc.a.h_out = h;
+  if (sc.tail_smem > 48 * 1024) {
+    set_error("N=%d too large for the fused tail kernel", N);
+    return HD_E_INVALID;
+  }
+  HD_CHECK_CUDA(launch_pdl(sampler_tail_k<true>, dim3(B), dim3(256), sc.tail_smem, sc.c.stream, sc.a));
+  count_launch();
   return HD_OK;
 }
 

@@ -82,6 +82,10 @@ struct Layout {
   int64_t fuse_tmp;  // [2H][2H] fp32 scratch of pack_weights
   int64_t emb_wT;  // [Fi][H]
   int64_t emb_b;   // [H]
+  // embedding folded into the first sub-layer's pre-projection (tensor-core engines, sampling loop):
+  //   A|B(embedding(in)) = in . emb_abT + emb_abb,  emb_abT = -log2(e) * (W1ab . W_emb)^T, emb_abb = -log2(e) * (W1ab . b_emb + [b1 | 0])
+  int64_t emb_abT; // [Fi][2H]
+  int64_t emb_abb; // [2H]
   int64_t out_w;   // [Fi][H] (as in the state_dict)
   int64_t out_b;   // [Fi] (+pad)
   std::vector<SubLayer> subs;
@@ -108,6 +112,8 @@ struct Workspace {
   int64_t hout;   // [BN][Fi]
   int64_t eps_raw;// [BN][3+F]
   int64_t nanflag;// [1] int32 per forward
+  int64_t state;  // [4] int32: sampling-loop state {step (advanced by the tail kernel), step of the running forward
+                  // (latched by out_vel_k), NaN flag of even steps, NaN flag of odd steps}
   int64_t node_off;// [B+1] int32: prefix of n_b (ragged node rows of the sampling path, tensor-core engines)
   int64_t row_off;// [B+1] int32: prefix of n_b * pad8(n_b) (edge rows per molecule, tensor-core engines)
   int64_t total_bytes;

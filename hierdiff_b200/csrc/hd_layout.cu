@@ -69,6 +69,8 @@ bool make_layout(const hd_config& c, Layout* out) {
   L.fuse_tmp = put((int64_t)2 * H * 2 * H * 4);
   L.emb_wT = put(Fi * H * 4);
   L.emb_b = put(H * 4);
+  L.emb_abT = put(Fi * 2 * H * 4);
+  L.emb_abb = put(2 * H * 4);
   L.out_w = put(Fi * H * 4);
   L.out_b = put(Fi * 4);
   for (int b = 0; b < c.n_layers; ++b) {
@@ -164,6 +166,7 @@ Workspace make_workspace(const hd_config& c, int B, int N) {
   W.hout = put(BN * Fi * 4);
   W.eps_raw = put(BN * (3 + Fi) * 4);
   W.nanflag = put(256);
+  W.state = put(256);
   W.row_off = put(((int64_t)B + 1) * 4);
   W.node_off = put(((int64_t)B + 1) * 4);
   W.total_bytes = p;
@@ -214,6 +217,23 @@ __global__ void fuse_k(const float* __restrict__ w1n, int ld1, const float* __re
     bm[o] = scale * (float)b;
   }
 }
+// Embedding folded into the first pre-projection:  A|B(W_emb in + b_emb) = (W1ab W_emb) in + (W1ab b_emb + [b1 | 0]).
+// outT[f][o] = scale * sum_j W1ab[o][j] * W_emb[j][f],  outb[o] = scale * (sum_j W1ab[o][j] * b_emb[j] + (o < H ? b1[o] : 0))
+__global__ void fuse_embed_k(const float* __restrict__ w1, int ld1, const float* __restrict__ b1,
+                             const float* __restrict__ emb_w, const float* __restrict__ emb_b, int Fi,
+                             float* __restrict__ outT, float* __restrict__ outb, float scale) {
+  const int o = blockIdx.x, f = threadIdx.x;   // grid 2H, block Fi + 1 (thread Fi: the bias)
+  const float* wrow = w1 + (int64_t)(o % H) * ld1 + (o / H) * H;
+  double acc = 0.0;
+  if (f < Fi) {
+    for (int j = 0; j < H; ++j) acc += (double)wrow[j] * (double)emb_w[(int64_t)j * Fi + f];
+    outT[(int64_t)f * 2 * H + o] = (float)((double)scale * acc);
+  } else {
+    acc = o < H ? (double)b1[o] : 0.0;
+    for (int j = 0; j < H; ++j) acc += (double)wrow[j] * (double)emb_b[j];
+    outb[o] = (float)((double)scale * acc);
+  }
+}
 // bf16 hi/lo operand image of rows [row0, row0+rows) x K columns [col0, col0+K) of src (ld):
 // img[kg][r][e] (kg < K/8, r < rows, e < 8)
 __global__ void image_k(const float* __restrict__ src, int ld, int row0, int col0, int rows, int K,
@@ -238,6 +258,8 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
   copy_k<<<grid(H), T, 0, st>>>(w + L.s_emb_b, H, F(L.emb_b));
   copy_k<<<grid(Fi * H), T, 0, st>>>(w + L.s_out_w, Fi * H, F(L.out_w));
   copy_k<<<grid(Fi), T, 0, st>>>(w + L.s_out_b, Fi, F(L.out_b));
+  fuse_embed_k<<<2 * H, Fi + 1, 0, st>>>(w + L.subs[0].s_w1, 2 * H + 2, w + L.subs[0].s_b1, w + L.s_emb_w, w + L.s_emb_b,
+                                        Fi, F(L.emb_abT), F(L.emb_abb), NEG_LOG2E);
   for (size_t si = 0; si < L.subs.size(); ++si) {
     const SubLayer& S = L.subs[si];
     const int ld1 = 2 * H + 2;

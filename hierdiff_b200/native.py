@@ -19,7 +19,7 @@ FLAG_NAN = 1
 FLAG_COG = 2
 FLAG_MASK = 4
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class HdConfig(ctypes.Structure):
@@ -62,6 +62,10 @@ SIGNATURES = {
     "hd_final_scalars": (_I, [_P, _I, _P, _P]),
     "hd_reverse_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
     "hd_final_decode": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _F, _F, _F, _P, _P, _P]),
+    "hd_sampler_begin": (_I, [_CFG, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "hd_sampler_step": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "hd_sampler_final": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P,
+                              _I, _P]),
     "hd_loop_fetch": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
 }
 

@@ -5,7 +5,7 @@ One reverse step of the reference is ~500 ATen launches, 8 host synchronisations
 host->device copy.  Here a step is a fixed sequence of native kernels plus the two
 ``normal_`` launches that draw the step's noise from torch's CUDA generator in the reference's order
 (``randn(B,N,3)`` then ``randn(B,N,F)``, diffusion_qm9.py:449-454).  Time and schedule scalars are read
-on the device through a step counter, so the same captured graph is replayed for every step; the
+on the device through a device-side step index, so the same captured graph is replayed for every step; the
 status word (NaN guard, mask / centre-of-gravity invariants) is read once after the loop.
 """
 import os
@@ -68,7 +68,14 @@ class ScheduleTable:
 
 
 class SamplingLoop:
-    """Static buffers + captured graph for one padded batch shape (B, N)."""
+    """Static buffers + captured graph for one padded batch shape (B, N).
+
+    A reverse step is: the two ``normal_`` launches that draw the step's noise from torch's CUDA generator (the
+    reference's ``randn(B,N,3)`` then ``randn(B,N,F)``, diffusion_qm9.py:449-454 - they stay torch calls so that the
+    Philox stream is the reference's), then ``hd_sampler_step``: the EGNN stack and ONE kernel for everything between
+    two stacks (centre-of-gravity projection, NaN guard, reverse update, step counter, the next forward's masking /
+    time channel / embedding / first pre-projection).  The step index lives on the device, so one captured graph
+    serves all T steps."""
 
     def __init__(self, model, B, N, device, steps_per_graph=8, use_graph=True):
         self.model, self.B, self.N, self.device = model, B, N, device
@@ -76,15 +83,12 @@ class SamplingLoop:
         D = 3 + self.F
         f32 = dict(dtype=torch.float32, device=device)
         self.z = torch.zeros(B, N, D, **f32)
-        self.eps = torch.zeros(B, N, D, **f32)
         self.rx = torch.zeros(B, N, 3, **f32)
         self.rh = torch.zeros(B, N, self.F, **f32)
-        self.t_cur = torch.zeros(B, **f32)
-        self.sched_cur = torch.zeros(B, 3, **f32)     # this step's scalars, one row per molecule
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
         self.flags = torch.zeros(1, dtype=torch.int32, device=device)
         self.sizes = torch.full((B,), N, dtype=torch.int32, device=device)
         C = model.dynamics.context_node_nf
+        self.C = C
         self.context = torch.zeros(B, N, C, **f32) if C else None   # static buffer read by the captured graph
         self.x_out = torch.zeros(B, N, 3, **f32)
         self.h_out = torch.zeros(B, N, self.F, **f32)
@@ -108,47 +112,52 @@ class SamplingLoop:
         (~3000 rows) and a good part of them is padding; below that it only adds set-up work."""
         return B * N >= 3072 and int(sum(int(v) for v in sizes_host)) <= 0.75 * B * N
 
-    # -- one reverse step, everything enqueued on the current stream --------------------------------
+    # -- native calls, everything enqueued on the current stream ------------------------------------
+    def _common(self):
+        egnn = self.model.dynamics.egnn
+        engine = egnn.engine_id() | (native.ENGINE_RAGGED_ROWS if self.ragged else 0)
+        return (egnn.hd_config(), native.ptr(egnn.packed_weights()), native.ptr(egnn.workspace(self.B, self.N, self.device)),
+                engine, int(self.live_rows) if self.ragged else 0)
+
+    def _begin(self):
+        """Input side of the first forward from ``self.z`` (= z_T); resets the device-side step index."""
+        cfg, packed, ws, engine, live = self._common()
+        native.check(native.lib().hd_sampler_begin(
+            cfg, packed, native.ptr(self.z), native.ptr(self.table.t), self.table.T, native.ptr(self.context), self.C,
+            native.ptr(self.sizes), self.B, self.N, live, ws, native.ptr(self.flags), engine, native.stream_ptr()),
+            "hd_sampler_begin")
+
     def _step(self):
-        L, m = native.lib(), self.model
-        st = native.stream_ptr()
-        native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
-                                     self.B, self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st),
-                     "hd_loop_fetch")
-        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
-                                 ragged=self.ragged, live_rows=self.live_rows)
+        cfg, packed, ws, engine, live = self._common()
         self.rx.normal_()
         self.rh.normal_()
-        native.check(L.hd_reverse_step(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
-                                       native.ptr(self.rh), native.ptr(self.sizes), self.B, self.N, self.F,
-                                       native.ptr(self.sched_cur), 1, native.ptr(self.z), native.ptr(self.flags),
-                                       st), "hd_reverse_step")
+        native.check(native.lib().hd_sampler_step(
+            cfg, packed, native.ptr(self.z), native.ptr(self.rx), native.ptr(self.rh), native.ptr(self.table.t),
+            native.ptr(self.table.sched), self.B, self.table.T, native.ptr(self.context), self.C,
+            native.ptr(self.sizes), self.B, self.N, live, ws, native.ptr(self.flags), engine, native.stream_ptr()),
+            "hd_sampler_step")
 
     def _final(self, norm=None):
         """``norm``: (norm_x, norm_h, bias_h) of ``unnormalize`` (diffusion_qm9.py:174-179); default: the model's."""
-        L, m = native.lib(), self.model
-        st = native.stream_ptr()
-        native.check(L.hd_loop_fetch(native.ptr(self.counter), native.ptr(self.table.t), native.ptr(self.table.sched),
-                                     self.B, self.B, native.ptr(self.t_cur), native.ptr(self.sched_cur), st),
-                     "hd_loop_fetch")
-        m.dynamics.forward_sizes(self.t_cur, self.z, self.sizes, flags=self.flags, out=self.eps, context=self.context,
-                                 ragged=self.ragged, live_rows=self.live_rows)
+        m = self.model
+        cfg, packed, ws, engine, live = self._common()
         self.rx.normal_()
         self.rh.normal_()
         nx, nh, bh = norm if norm is not None else (m.norm_values[0], m.norm_values[1], m.norm_biases[1])
-        native.check(L.hd_final_decode(native.ptr(self.z), native.ptr(self.eps), native.ptr(self.rx),
-                                       native.ptr(self.rh), native.ptr(self.sizes), self.B, self.N, self.F,
-                                       native.ptr(self.sched_cur), 1, float(nx), float(nh), float(bh),
-                                       native.ptr(self.x_out), native.ptr(self.h_out), st), "hd_final_decode")
+        native.check(native.lib().hd_sampler_final(
+            cfg, packed, native.ptr(self.z), native.ptr(self.rx), native.ptr(self.rh), native.ptr(self.table.t),
+            native.ptr(self.table.sched), self.B, self.table.T, native.ptr(self.context), self.C,
+            native.ptr(self.sizes), self.B, self.N, live, float(nx), float(nh), float(bh), native.ptr(self.x_out),
+            native.ptr(self.h_out), ws, native.ptr(self.flags), engine, native.stream_ptr()), "hd_sampler_final")
 
     def _capture(self, k):
         # warm-up on a side stream (also packs weights / allocates the workspace outside the capture)
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
-        saved = self.z.clone(), self.counter.clone(), self.flags.clone()
+        saved = self.z.clone(), self.flags.clone()
         rng = torch.cuda.get_rng_state(self.device)  # the warm-up step must not consume the sample's noise stream
         with torch.cuda.stream(s):
-            self.counter.zero_()
+            self._begin()
             self._step()
         torch.cuda.current_stream(self.device).wait_stream(s)
         g = torch.cuda.CUDAGraph()
@@ -156,8 +165,7 @@ class SamplingLoop:
             for _ in range(k):
                 self._step()
         self.z.copy_(saved[0])
-        self.counter.copy_(saved[1])
-        self.flags.copy_(saved[2])
+        self.flags.copy_(saved[1])
         torch.cuda.synchronize(self.device)
         torch.cuda.set_rng_state(rng, self.device)
         self._graphs[(self.ragged, self.live_rows)], self.graph_steps = g, k
@@ -197,7 +205,6 @@ class SamplingLoop:
             if context is not None:
                 self.context.copy_(torch.as_tensor(context, dtype=torch.float32).expand_as(self.context),
                                    non_blocking=True)
-            self.counter.zero_()
             self.flags.zero_()
             if z_T is None:
                 # z_T ~ sample_combined_position_feature_noise (diffusion_qm9.py:361)
@@ -211,6 +218,7 @@ class SamplingLoop:
             nvtx = os.environ.get("HD_NVTX") == "1"    # ranges for nsys / ncu --nvtx captures
             if nvtx:
                 torch.cuda.nvtx.range_push(f"hierdiff.chain B={self.B} N={self.N} T={T}")
+            self._begin()
             done = 0
             if self.graph is not None:
                 while done + self.graph_steps <= T:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 4
+#define HD_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -176,6 +176,35 @@ HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* 
  * pass sched_per_mol = 1 to hd_reverse_step / hd_final_decode) or 1 (one row for the whole batch). */
 HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B,
                       int32_t sched_rows, float* t_cur, float* sched_cur, hd_stream_t stream);
+
+/* The T-step loop of DiffusionQM9.sample (diffusion_qm9.py:361-386) with everything BETWEEN two EGNN stacks in one
+ * kernel.  A chain is: hd_sampler_begin, T x hd_sampler_step, hd_sampler_final; the step index lives in `workspace`
+ * (reset by _begin, advanced on the device by every _step), so one captured CUDA graph of a step serves all T.
+ *   t_table [T+1]: time fed to the dynamics by the k-th executed forward (t/T for the steps, 0 for the final decode);
+ *   sched_table [T+1][sched_rows][3], sched_rows = B or 1: row k < T = hd_step_scalars of the k-th executed step,
+ *   row T = hd_final_scalars;  z [B,N,3+F] is updated in place;  randn_x / randn_h: this step's two raw draws.
+ * _begin:  the input side of the first forward (en_dynamics.py:56-79 masking, time / context channels; egnn_new.py:197
+ *          embedding, with the first sub-layer's pre-projection folded through it) from z = z_T.
+ * _step:   the EGNN blocks and output head of the forward prepared by the previous call, then ONE kernel for:
+ *          NaN guard + centre-of-gravity projection (en_dynamics.py:109-116), sample_p_zs_given_zt
+ *          (diffusion_qm9.py:328-345, as hd_reverse_step, same status bits), step counter, the next forward's input side.
+ * _final:  the last forward (t = 0) and sample_p_xh_given_z0 (diffusion_qm9.py:294-310, as hd_final_decode).
+ * live_rows / HD_ENGINE_RAGGED_ROWS as hd_dynamics_forward_ragged.  N is limited by the tail kernel's shared memory
+ * (3*N*(3+F) floats <= 48 KB). */
+HD_API int32_t hd_sampler_begin(const hd_config* cfg, const void* packed, const float* z, const float* t_table, int32_t T,
+                                const float* context, int32_t context_nf, const int32_t* sizes, int32_t B, int32_t N,
+                                int32_t live_rows, void* workspace, int32_t* flags, int32_t engine, hd_stream_t stream);
+HD_API int32_t hd_sampler_step(const hd_config* cfg, const void* packed, float* z, const float* randn_x,
+                               const float* randn_h, const float* t_table, const float* sched_table, int32_t sched_rows,
+                               int32_t T, const float* context, int32_t context_nf, const int32_t* sizes, int32_t B,
+                               int32_t N, int32_t live_rows, void* workspace, int32_t* flags, int32_t engine,
+                               hd_stream_t stream);
+HD_API int32_t hd_sampler_final(const hd_config* cfg, const void* packed, const float* z, const float* randn_x,
+                                const float* randn_h, const float* t_table, const float* sched_table,
+                                int32_t sched_rows, int32_t T, const float* context, int32_t context_nf,
+                                const int32_t* sizes, int32_t B, int32_t N, int32_t live_rows, float norm_x,
+                                float norm_h, float bias_h, float* x, float* h, void* workspace, int32_t* flags,
+                                int32_t engine, hd_stream_t stream);
 
 /* Profiling hook: enqueue ONLY the fused edge kernel of sub-layer (block, sub) - sub == inv_sublayers selects
  * the EquivariantUpdate - on the operands a previous hd_gcl_forward / hd_equiv_update call left in `workspace`

@@ -23,28 +23,40 @@ static void run(const char* name, hd::tc::Params p) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0;
   for (int it = 0; it < 3; ++it) {
+#ifdef HD_PHASE_TIMING
     cudaMemcpyToSymbol(tc::g_acc, zero, sizeof(zero));
+#endif
     cudaEventRecord(e0);
+#ifdef HD_TIMING_SLAB
+    for (int k = 0; k < 10; ++k) tc::launch_edge<GCL, STRICT, 2, false, true>(p, 0);
+#else
     for (int k = 0; k < 10; ++k) tc::launch_edge<GCL, STRICT, 2>(p, 0);
+#endif
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     cudaEventElapsedTime(&ms, e0, e1);
   }
-  long long acc2[2][3][16];
+  long long acc2[2][3][16] = {};
+#ifdef HD_PHASE_TIMING
   cudaMemcpyFromSymbol(acc2, tc::g_acc, sizeof(acc2));
+#else
+  (void)zero;
+  printf("%s: %.2f us/launch; err=%s\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
+  return;
+#endif
   for (int cta = 0; cta < 2; ++cta) {
   long long (*acc)[16] = acc2[cta];
   printf(" -- CTA %d (cluster rank %d)\n", 10 + cta, cta);
   printf("%s: %.2f us/launch; err=%s  (cycles per launch)\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
     const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier", "issue loads"};
   const char* en[] = {"wait accumulator", "pass 1", "dot exchange", "pass 2", "scratch barrier", "combine+release"};
-  const char* mn[] = {"wait free acc", "wait operands", "issue"};
+  const char* mn[] = {"wait free acc", "wait operands", "issue", "wait W2-lo chunk", "wait peer's chunk"};
   long long s = 0;
   for (int i = 0; i < 6; ++i) { printf("  producer  %-20s %8lld\n", pn[i], acc[0][i] / 10); s += acc[0][i] / 10; }
   printf("  producer  total %lld\n", s); s = 0;
   for (int i = 0; i < 6; ++i) { printf("  epilogue  %-20s %8lld\n", en[i], acc[1][i] / 10); s += acc[1][i] / 10; }
   printf("  epilogue  total %lld\n", s); s = 0;
-  for (int i = 0; i < 3; ++i) { printf("  mma       %-20s %8lld\n", mn[i], acc[2][i] / 10); s += acc[2][i] / 10; }
+  for (int i = 0; i < 5; ++i) { printf("  mma       %-20s %8lld\n", mn[i], acc[2][i] / 10); s += acc[2][i] / 10; }
   printf("  mma       total %lld\n", s);
   }
 }
