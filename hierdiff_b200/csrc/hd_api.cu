@@ -443,50 +443,64 @@ struct SamplerArgs {
 
 // Input side of an EGNN forward for molecule b from its z rows in shared memory (zv [N][D]): x, x0 (masked), the
 // embedding h and, for the tensor-core engines, the first sub-layer's A|B operands.  row0 = first workspace row of the
-// molecule.  Called by all 256 threads of the block; thread = channel.  The thread keeps its columns of the (folded)
-// embedding weights in registers and walks over the nodes without any barrier.
+// molecule; inp = shared scratch [N][EMB_FMAX].  Called by all 256 threads of the block; thread = channel.  The thread
+// keeps its columns of the (folded) embedding weights in registers and walks over the nodes without any barrier.
+constexpr int EMB_FMAX = 12;               // input channels (F + time + context) held in registers; more: re-read
 __device__ __forceinline__ void embed_molecule(const SamplerArgs& p, const float* zv, int b, int n, int64_t row0,
-                                               float t) {
-  constexpr int FMAX = 12;                  // input channels held in registers (F + time + context); more: re-read
+                                               float t, float* inp) {
   const int N = p.N, F = p.F, C = p.C, D = 3 + F, Fi = F + 1 + C, tid = threadIdx.x;
   const int64_t rows = (int64_t)p.B * N;
   const int count = p.ragged ? n : N;      // ragged node rows: padded nodes own no row
   const bool ab = p.emb_abT != nullptr;
-  for (int idx = tid; idx < count * 3; idx += 256) {
-    const int i = idx / 3, ch = idx - 3 * i;
-    const float v = i < n ? zv[i * D + ch] : 0.f;
-    p.x[(row0 + i) * 3 + ch] = v;
-    p.x0[(row0 + i) * 3 + ch] = v;
+  // per-node input vectors [features * mask | t | context], zero-padded to EMB_FMAX (time and context are not masked,
+  // en_dynamics.py:66-79), and the masked coordinates
+  for (int i = tid >> 4; i < count; i += 16) {
+    const int f = tid & 15;
+    if (f < EMB_FMAX) {
+      float v = 0.f;
+      if (i < n) {
+        if (f < F) v = zv[i * D + 3 + f];
+        else if (f == F) v = t;
+        else if (f < Fi) v = p.context[((int64_t)b * N + i) * C + (f - F - 1)];
+      }
+      inp[i * EMB_FMAX + f] = v;
+    } else if (f < EMB_FMAX + 3) {
+      const int ch = f - EMB_FMAX;
+      const float v = i < n ? zv[i * D + ch] : 0.f;
+      p.x[(row0 + i) * 3 + ch] = v;
+      p.x0[(row0 + i) * 3 + ch] = v;
+    }
   }
-  float w[FMAX], wa[FMAX], wb[FMAX];
+  float w[EMB_FMAX], wa[EMB_FMAX], wb[EMB_FMAX];
 #pragma unroll
-  for (int f = 0; f < FMAX; ++f) {
+  for (int f = 0; f < EMB_FMAX; ++f) {
     w[f] = f < Fi ? p.emb_wT[f * H + tid] : 0.f;
     wa[f] = ab && f < Fi ? p.emb_abT[f * 2 * H + tid] : 0.f;
     wb[f] = ab && f < Fi ? p.emb_abT[f * 2 * H + H + tid] : 0.f;
   }
   const float bias = p.emb_b[tid], bias_a = ab ? p.emb_abb[tid] : 0.f, bias_b = ab ? p.emb_abb[H + tid] : 0.f;
-  for (int i = 0; i < count; ++i) {
-    const int64_t o = row0 + i;
+  __syncthreads();
+  float* hp = p.h + row0 * H + tid;
+  // K-chunk-major operand image of the edge kernel: [col / 16][row][col % 16], A (cols 0..H-1) then B
+  float* ap = p.ab + ((int64_t)(tid >> 4) * rows + row0) * 16 + (tid & 15);
+  float* bp = p.ab + ((int64_t)((H + tid) >> 4) * rows + row0) * 16 + (tid & 15);
+  for (int i = 0; i < count; ++i, hp += H, ap += 16, bp += 16) {
     float v = 0.f, a0 = 0.f, a1 = 0.f;
     if (i < n) {
       v = bias;
       a0 = bias_a;
       a1 = bias_b;
-      const float* zi = zv + i * D + 3;     // the F feature channels (shared memory, broadcast reads)
-      const float* ci = p.context + ((int64_t)b * N + i) * C;
+      const float4* in4 = reinterpret_cast<const float4*>(inp + i * EMB_FMAX);   // broadcast reads
 #pragma unroll
-      for (int f = 0; f < FMAX; ++f) {
-        if (f < Fi) {
-          // time and context are not masked (en_dynamics.py:66-79)
-          const float in = f < F ? zi[f] : (f == F ? t : ci[f - F - 1]);
-          v = fmaf(in, w[f], v);
-          a0 = fmaf(in, wa[f], a0);
-          a1 = fmaf(in, wb[f], a1);
-        }
+      for (int q = 0; q < EMB_FMAX / 4; ++q) {
+        const float4 in = in4[q];
+        v = fmaf(in.x, w[4 * q], v);          a0 = fmaf(in.x, wa[4 * q], a0);          a1 = fmaf(in.x, wb[4 * q], a1);
+        v = fmaf(in.y, w[4 * q + 1], v);      a0 = fmaf(in.y, wa[4 * q + 1], a0);      a1 = fmaf(in.y, wb[4 * q + 1], a1);
+        v = fmaf(in.z, w[4 * q + 2], v);      a0 = fmaf(in.z, wa[4 * q + 2], a0);      a1 = fmaf(in.z, wb[4 * q + 2], a1);
+        v = fmaf(in.w, w[4 * q + 3], v);      a0 = fmaf(in.w, wa[4 * q + 3], a0);      a1 = fmaf(in.w, wb[4 * q + 3], a1);
       }
-      for (int f = FMAX; f < Fi; ++f) {    // wider inputs than the register file holds: weights re-read per node
-        const float in = f < F ? zi[f] : (f == F ? t : ci[f - F - 1]);
+      for (int f = EMB_FMAX; f < Fi; ++f) {   // wider inputs than the register file holds: re-read per node
+        const float in = f < F ? zv[i * D + 3 + f] : (f == F ? t : p.context[((int64_t)b * N + i) * C + (f - F - 1)]);
         v = fmaf(in, __ldg(p.emb_wT + f * H + tid), v);
         if (ab) {
           a0 = fmaf(in, __ldg(p.emb_abT + f * 2 * H + tid), a0);
@@ -494,20 +508,33 @@ __device__ __forceinline__ void embed_molecule(const SamplerArgs& p, const float
         }
       }
     }
-    p.h[o * H + tid] = v;
-    if (ab) {   // K-chunk-major operand image of the edge kernel: [col / 16][row][col % 16], A then B
-      p.ab[((int64_t)(tid >> 4) * rows + o) * 16 + (tid & 15)] = a0;
-      p.ab[((int64_t)((H + tid) >> 4) * rows + o) * 16 + (tid & 15)] = a1;
+    *hp = v;
+    if (ab) {
+      *ap = a0;
+      *bp = a1;
     }
   }
 }
+
+// element loop over a molecule's [N][D] block without integer division when D <= 16: 16 threads per node
+#define HD_FOR_EACH_ELEM(i, ch, N, D, body)                                              \
+  if ((D) <= 16) {                                                                       \
+    const int ch = threadIdx.x & 15;                                                     \
+    if (ch < (D))                                                                        \
+      for (int i = threadIdx.x >> 4; i < (N); i += (int)(blockDim.x >> 4)) { body }      \
+  } else {                                                                               \
+    for (int _e = threadIdx.x; _e < (N) * (D); _e += blockDim.x) {                        \
+      const int i = _e / (D), ch = _e - i * (D);                                         \
+      body                                                                               \
+    }                                                                                    \
+  }
 
 // First kernel of a chain: loop state, the prefix tables of the edge kernel / ragged layout, and the input side of the
 // first forward.  One CTA per molecule, 256 threads.
 __global__ void __launch_bounds__(256) sampler_begin_k(const SamplerArgs p) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sm[];   // zv [N*D]
+  extern __shared__ float sm[];   // inp [N*EMB_FMAX] (16-byte aligned rows), zv [N*D]
   __shared__ int s_part[8];
   const int D = 3 + p.F, b = blockIdx.x, tid = threadIdx.x, n = p.sizes[b];
   if (b == 0 && tid < 32) {
@@ -554,11 +581,12 @@ __global__ void __launch_bounds__(256) sampler_begin_k(const SamplerArgs p) {
     row0 = base;
   }
   const float* zsrc = p.z + (int64_t)b * p.N * D;
-  for (int idx = tid; idx < p.N * D; idx += 256) sm[idx] = zsrc[idx];
+  float* zv = sm + p.N * EMB_FMAX;
+  for (int idx = tid; idx < p.N * D; idx += 256) zv[idx] = zsrc[idx];
   // x2, the ping-pong partner of the coordinate updates: padded rows must be 0 and are never written afterwards
   for (int idx = tid; idx < (p.ragged ? n : p.N) * 3; idx += 256) p.x2[row0 * 3 + idx] = 0.f;
   __syncthreads();
-  embed_molecule(p, sm, b, n, row0, p.t_table[0]);
+  embed_molecule(p, zv, b, n, row0, p.t_table[0], sm);
 }
 
 // Between two forwards (FINAL: after the last one).  One CTA per molecule, 256 threads.
@@ -566,12 +594,12 @@ template <bool FINAL>
 __global__ void __launch_bounds__(256) sampler_tail_k(const SamplerArgs p) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sm[];  // nz [N*D], ev [N*D], zv [N*D]
+  extern __shared__ float sm[];  // nz [N*D], ev [N*D], zv [N*D]; nz is reused as the embedding's input scratch
   __shared__ float s_mean[3];
   __shared__ float s_chk[3];
   const int N = p.N, F = p.F, D = 3 + F, b = blockIdx.x, tid = threadIdx.x, n = p.sizes[b];
   float* nz = sm;
-  float* ev = sm + N * D;
+  float* ev = sm + N * max(D, EMB_FMAX);
   float* zv = ev + N * D;
   const int k = min(p.state[1], p.T);          // the step whose forward has just run (latched by out_vel_k)
   const bool nan = p.state[2 + (k & 1)] != 0;  // NaN guard of that forward (whole batch, en_dynamics.py:109-111)
@@ -579,40 +607,47 @@ __global__ void __launch_bounds__(256) sampler_tail_k(const SamplerArgs p) {
   const float c0 = sc[0], c1 = sc[1], c2 = sc[2];
   const float* zsrc = p.z + (int64_t)b * N * D;
   const float* esrc = p.eps_raw + (int64_t)b * N * D;
+  const float* rxs = p.rx + (int64_t)b * N * 3;
+  const float* rhs = p.rh + (int64_t)b * N * F;
   if (tid < 3) s_chk[tid] = 0.f;
-  load_noise(p.rx + (int64_t)b * N * 3, p.rh + (int64_t)b * N * F, N, F, n, nz, s_mean);
+  // the step's noise (diffusion_qm9.py:445-456: masked, positions centred below), z_t and eps into shared memory
   float pad_abs = 0.f, max_abs = 0.f;
-  for (int idx = tid; idx < N * D; idx += 256) {
+  HD_FOR_EACH_ELEM(i, ch, N, D, {
+    const int idx = i * D + ch;
+    const float mk = i < n ? 1.f : 0.f;
+    nz[idx] = (ch < 3 ? rxs[i * 3 + ch] : rhs[i * F + (ch - 3)]) * mk;
     const float v = zsrc[idx];
     zv[idx] = v;
     float e = esrc[idx];
-    if (nan && idx % D < 3) e = 0.f;
+    if (nan && ch < 3) e = 0.f;
     ev[idx] = e;
-    if (idx % D < 3) {
-      if (idx / D >= n) pad_abs = fmaxf(pad_abs, fabsf(v));
+    if (ch < 3) {
+      if (i >= n) pad_abs = fmaxf(pad_abs, fabsf(v));
       max_abs = fmaxf(max_abs, fabsf(v));
     }
-  }
+  })
   if (nan && p.flags && b == 0 && tid == 0) atomicOr(p.flags, HD_FLAG_NAN);
   __syncthreads();
-  float mean[3];
-  block_mean3(ev, N, D, n, s_mean, mean);      // remove_mean_with_mask that ends _forward (en_dynamics.py:116)
-  for (int idx = tid; idx < N * 3; idx += 256) {
-    const int i = idx / 3, ch = idx % 3;
-    if (i < n) ev[i * D + ch] -= mean[ch];
+  float mean[3], emean[3];
+  block_mean3(nz, N, D, n, s_mean, mean);      // sample_center_gravity_zero_gaussian_with_mask (models/utils.py:126-135)
+  block_mean3(ev, N, D, n, s_mean, emean);     // remove_mean_with_mask that ends _forward (en_dynamics.py:116)
+  for (int idx = tid; idx < n * 3; idx += 256) {
+    const int i = idx / 3, ch = idx - 3 * i;
+    nz[i * D + ch] -= mean[ch];
+    ev[i * D + ch] -= emean[ch];
   }
   __syncthreads();
   if (FINAL) {
     // sample_p_xh_given_z0 (diffusion_qm9.py:294-310, :174-179): {alpha_0, sigma_0, sigma_x} = c0, c1, c2
-    for (int idx = tid; idx < N * D; idx += 256) {
-      const int i = idx / D, ch = idx % D;
+    HD_FOR_EACH_ELEM(i, ch, N, D, {
+      const int idx = i * D + ch;
       if (ch < 3) {
         const float mu = 1.0f / c0 * (zv[idx] - c1 * ev[idx]);   // :244
         p.x_out[((int64_t)b * N + i) * 3 + ch] = (mu + c2 * nz[idx]) * p.norm_x;
       } else {
         p.h_out[((int64_t)b * N + i) * F + (ch - 3)] = (zv[idx] * p.norm_h + p.bias_h) * (i < n ? 1.f : 0.f);
       }
-    }
+    })
     return;
   }
   // sample_p_zs_given_zt after the network call (diffusion_qm9.py:328-345): {alpha_t|s, sigma2_t|s/alpha_t|s/sigma_t,
@@ -630,27 +665,27 @@ __global__ void __launch_bounds__(256) sampler_tail_k(const SamplerArgs p) {
     if (f) atomicOr(p.flags, f);
   }
   block_mean3(ev, N, D, n, s_mean, mean);      // :330 second CoG removal on eps_x
-  for (int idx = tid; idx < N * D; idx += 256) {
-    const int i = idx / D, ch = idx % D;
+  HD_FOR_EACH_ELEM(i, ch, N, D, {
+    const int idx = i * D + ch;
     float e = ev[idx];
     if (ch < 3 && i < n) e -= mean[ch];
     const float mu = zv[idx] / c0 - c1 * e;    // :331
     zv[idx] = mu + c2 * nz[idx];               // :337, :442
-  }
+  })
   __syncthreads();
   block_mean3(zv, N, D, n, s_mean, mean);      // :340-344
   float* dst = p.z + (int64_t)b * N * D;
-  for (int idx = tid; idx < N * D; idx += 256) {
-    const int i = idx / D, ch = idx % D;
+  HD_FOR_EACH_ELEM(i, ch, N, D, {
+    const int idx = i * D + ch;
     float v = zv[idx];
     if (ch < 3 && i < n) v -= mean[ch];
     zv[idx] = v;
     dst[idx] = v;
-  }
+  })
   if (b == 0 && tid == 0) p.state[0] = k + 1;  // read by the next forward's out_vel_k only
   __syncthreads();
   const int64_t row0 = p.ragged ? p.node_off[b] : (int64_t)b * N;
-  embed_molecule(p, zv, b, n, row0, p.t_table[min(k + 1, p.T)]);
+  embed_molecule(p, zv, b, n, row0, p.t_table[min(k + 1, p.T)], nz);
 }
 
 __device__ __forceinline__ float softplus_t(float v) { return v > 20.0f ? v : log1pf(expf(v)); }  // F.softplus
@@ -1021,7 +1056,7 @@ static int sampler_setup(SamplerCall* sc, const hd_config* cfg, const void* pack
   a.row_off = tc ? reinterpret_cast<int32_t*>(c.ws + c.W.row_off) : nullptr;
   a.node_off = const_cast<int32_t*>(c.node_off);
   a.rows_bound = live_rows > 0 ? live_rows : B * N;
-  sc->tail_smem = sizeof(float) * 3 * N * D;
+  sc->tail_smem = sizeof(float) * N * (2 * D + (D > EMB_FMAX ? D : EMB_FMAX));
   return HD_OK;
 }
 
@@ -1122,7 +1157,8 @@ HD_API int32_t hd_sampler_begin(const hd_config* cfg, const void* packed, const 
   int rc = sampler_setup(&sc, cfg, packed, const_cast<float*>(z), t_table, nullptr, 1, T, context, context_nf, sizes, B, N,
                          live_rows, workspace, flags, engine, stream);
   if (rc) return rc;
-  HD_CHECK_CUDA(launch_pdl(sampler_begin_k, dim3(B), dim3(256), sizeof(float) * N * (3 + sc.a.F), sc.c.stream, sc.a));
+  HD_CHECK_CUDA(launch_pdl(sampler_begin_k, dim3(B), dim3(256), sizeof(float) * N * (3 + sc.a.F + EMB_FMAX), sc.c.stream,
+                          sc.a));
   count_launch();
   return HD_OK;
 }

@@ -18,8 +18,6 @@
 //
 // Accumulators are double buffered in TMEM (2 x 256 columns), so tile t's epilogue overlaps tile t+1's MMAs
 // and tile t+2's operand generation.
-#include <cstdlib>
-
 #include <cuda_bf16.h>
 
 #include "hd_common.cuh"
@@ -70,38 +68,9 @@ constexpr bool FILL_HELP = false;
 constexpr bool FILL_HELP = true;    // the epilogue warps build half of the first tile's operand chunks (pipeline fill)
 #endif
 
-// SLAB variant (template parameter of the kernel): the A_i / B_j operand rows a tile needs are staged in shared memory
-// by bulk copies (TMA 1-D) issued one to three 32-column stages ahead, so the producers read them with LDS instead of
-// gathering 64-byte pieces from L2 with LDG (which cost them ~23 % of the kernel: the gathers stall on first use and
-// fence.proxy.async drains them at every stage hand-off).  To make room, the W2 lo image is streamed in 32-column
-// chunks instead of being resident.
-constexpr int SLAB_COLS = 32;                        // K columns per slab stage (two 16-column sub-chunks)
-constexpr int SLAB_PER_TILE = H / SLAB_COLS;         // 8
-constexpr int SLAB_SLOTS = 96;                       // operand rows (sender rows, then receiver rows) a stage can hold
-constexpr int SLAB_SUB = SLAB_SLOTS * 64;            // bytes of one 16-column sub-chunk of a stage
-constexpr int SLAB_STAGE = 2 * SLAB_SUB;             // 12 KB
-constexpr int NSLAB = 3;                             // slab ring depth
-constexpr int WLO_CHUNK = (SLAB_COLS / 8) * W_KG;    // 8 KB: 32 K-columns of one 128-row W2 lo half image
-constexpr int NWLO = 3;                              // W2 lo ring depth
-constexpr int MAX_SEG = 18;                          // molecules a 128-row tile can touch (each has >= 8 rows)
-constexpr int NTHREADS_SLAB = NTHREADS + 64;         // + slab copy warp + W2 lo copy warp
-
 struct PMeta {        // what the operand producers need of an edge row
   float r, d0;        // |x_i-x_j|^2, |x0_i-x0_j|^2
-  int recv, send;     // flat node rows b*N+i, b*N+j  (slab tiles: slab slots of A_i and B_j);  recv < 0: dead row
-};
-struct Seg {          // one molecule touched by a tile (slab staging)
-  int node0;          // workspace row of its node 0
-  int n;              // nodes = sender rows staged
-  int bslot;          // first slab slot of its sender rows
-  int i_lo, acnt;     // receivers i_lo .. i_lo + acnt - 1 of it appear in the tile
-  int aslot;          // first slab slot of those receiver rows (counted after all sender rows)
-};
-struct TileInfo {
-  int nseg;           // molecules touched
-  int slab;           // 1: operands staged in the slab ring; 0: gathered with LDG (too many distinct rows for a stage)
-  int rows;           // slots used (sender + receiver rows)
-  int pad;
+  int recv, send;     // flat node rows b*N+i, b*N+j
 };
 struct EMeta {        // what the epilogue needs of an edge row
   float cd0, cd1, cd2;  // (x_i-x_j)/(sqrt(r+1e-8)+norm_constant)  (EquivariantUpdate only)
@@ -126,39 +95,8 @@ struct Params {
   float range, norm_constant, norm_div;
 };
 
-template <bool STRICT, int CG, bool SLAB = false>
-struct Smem;
-
-template <bool STRICT>
-struct Smem<STRICT, 2, true> {
-  static constexpr int W_PARTS = 1;                                 // W2 hi resident; lo (strict) streamed
-  static constexpr int W_BYTES = W_HALF;
-  static constexpr int STAGE = A_HALF * (STRICT ? 2 : 1);
-  static constexpr int OFF_W = 0;
-  static constexpr int OFF_WLO = OFF_W + W_BYTES;                   // [NWLO][WLO_CHUNK]
-  static constexpr int OFF_A = OFF_WLO + (STRICT ? NWLO * WLO_CHUNK : 0);
-  static constexpr int OFF_SLAB = OFF_A + NSTAGE * STAGE;           // [NSLAB][2][SLAB_SLOTS][16] fp32
-  static constexpr int OFF_SCR = OFF_SLAB + NSLAB * SLAB_STAGE;     // [16][H] fp32
-  static constexpr int OFF_VEC = OFF_SCR + 16 * H * 4;              // b2, wa, wr, wd
-  static constexpr int OFF_ROW = OFF_VEC + 4 * H * 4;               // row_off [MAX_B+1]
-  static constexpr int OFF_PMETA = OFF_ROW + (MAX_B + 1) * 4;
-  static constexpr int OFF_EMETA = OFF_PMETA + PMETA_BUFS * TILE_M * (int)sizeof(PMeta);
-  static constexpr int OFF_GRP = OFF_EMETA + EMETA_BUFS * TILE_M * (int)sizeof(EMeta);
-  static constexpr int OFF_DOT = OFF_GRP + EMETA_BUFS * 16 * 8;
-  static constexpr int OFF_SEG = OFF_DOT + 2 * TILE_M * 4;          // Seg [EMETA_BUFS][MAX_SEG]
-  static constexpr int OFF_TINFO = OFF_SEG + EMETA_BUFS * MAX_SEG * (int)sizeof(Seg);   // TileInfo [EMETA_BUFS]
-  static constexpr int OFF_READY = OFF_TINFO + EMETA_BUFS * (int)sizeof(TileInfo);      // int: tiles whose Seg table is written
-  static constexpr int OFF_BAR = OFF_READY + 16;
-  // barriers: the 2*NSTAGE+10 of the plain kernel, then slab_full[NSLAB], slab_empty[NSLAB], wlo_full[NWLO],
-  // wlo_empty[NWLO], wlo_peer[NWLO]
-  static constexpr int NBAR = 2 * NSTAGE + 10 + 2 * NSLAB + 3 * NWLO;
-  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-  static constexpr int TOTAL = OFF_TMEM + 16;
-  static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
-};
-
 template <bool STRICT, int CG>
-struct Smem<STRICT, CG, false> {
+struct Smem {
 #ifdef HD_EXP_WLO_ALIAS   // timing experiment only (wrong numerics): no resident W2 lo image, the lo pass re-reads W2 hi
   static constexpr int W_PARTS = 1;
 #else
@@ -181,7 +119,6 @@ struct Smem<STRICT, CG, false> {
   static constexpr int NBAR = 2 * NSTAGE + 10;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
-  static constexpr int OFF_WLO = 0, OFF_SLAB = 0, OFF_SEG = 0, OFF_TINFO = 0, OFF_READY = 0;   // unused
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
@@ -251,12 +188,9 @@ __host__ __device__ constexpr float silu_kacc() { return STRICT ? 1.0f : -1.4426
 
 // WIDE: the variant for batches whose row table does not fit the shared-memory slot (B > MAX_B) and / or whose node
 // rows are ragged (p.node_off); the default instantiation carries neither branch.
-// SLAB: operand rows staged in shared memory by bulk copies, W2 lo streamed (see the constants above); needs CG == 2 and
-// a row table that fits shared memory (B <= MAX_B).
-template <bool GCL, bool STRICT, int CG, bool WIDE = false, bool SLAB = false>
-__global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(const Params p) {
-  using S = Smem<STRICT, CG, SLAB>;
-  constexpr int NT = SLAB ? NTHREADS_SLAB : NTHREADS;
+template <bool GCL, bool STRICT, int CG, bool WIDE = false>
+__global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
+  using S = Smem<STRICT, CG>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -282,24 +216,13 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
   const uint32_t bar_meta = bar0 + 8u * (2 * NSTAGE + 6), bar_tstart = bar0 + 8u * (2 * NSTAGE + 7);
   // one-shot pair for the helpers of the first tile: tile 0's metadata is ready / every helper warp has read it
   const uint32_t bar_meta0 = bar0 + 8u * (2 * NSTAGE + 8), bar_hmeta = bar0 + 8u * (2 * NSTAGE + 9);
-  constexpr int MMA_WARP = NPW + NEW, META_WARP = MMA_WARP + 1, COPY_WARP = META_WARP + 1, WLO_WARP = COPY_WARP + 1;
-  // SLAB: operand-row ring (copy warp -> producers) and W2 lo ring (W2-lo warp -> MMA issuer; wlo_peer: the peer CTA's
-  // chunk has landed too, forwarded by its idle MMA-warp thread)
-  constexpr int BAR_X = 2 * NSTAGE + 10;
-  auto slab_full = [&](int i) { return bar0 + 8u * (BAR_X + i); };
-  auto slab_empty = [&](int i) { return bar0 + 8u * (BAR_X + NSLAB + i); };
-  auto wlo_full = [&](int i) { return bar0 + 8u * (BAR_X + 2 * NSLAB + i); };
-  auto wlo_empty = [&](int i) { return bar0 + 8u * (BAR_X + 2 * NSLAB + NWLO + i); };
-  auto wlo_peer = [&](int i) { return bar0 + 8u * (BAR_X + 2 * NSLAB + 2 * NWLO + i); };
-  Seg* s_seg = reinterpret_cast<Seg*>(smem + S::OFF_SEG);
-  TileInfo* s_tinfo = reinterpret_cast<TileInfo*>(smem + S::OFF_TINFO);
-  volatile int* s_ready = reinterpret_cast<volatile int*>(smem + S::OFF_READY);
+  constexpr int MMA_WARP = NPW + NEW, META_WARP = MMA_WARP + 1;
 
   // ---- one-time setup --------------------------------------------------------------------------
   // Everything up to pdl_wait() touches only constants (weights) and on-chip state, so it overlaps the previous
   // kernel's tail: barrier init, the resident W2 image (TMA bulk copies, 64-128 KB), the bias / weight vectors, TMEM.
   pdl_trigger();
-  for (int k = tid; k < H; k += NT) {
+  for (int k = tid; k < H; k += NTHREADS) {
     s_b2[k] = p.b2[k];
     s_wa[k] = p.wa[k];
     s_wr[k] = p.wr[k];
@@ -320,18 +243,6 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
     ptx::mbar_init(bar_meta0, 1);
     ptx::mbar_init(bar_hmeta, NEW);
     ptx::mbar_init(bar_wr, CG);
-    if constexpr (SLAB) {
-      for (int i = 0; i < NSLAB; ++i) {
-        ptx::mbar_init(slab_full(i), 1);       // the copy warp's expect_tx arrive; completed by the bulk copies
-        ptx::mbar_init(slab_empty(i), NPW);    // one elected arrive per warp of the group that consumed the stage
-      }
-      for (int i = 0; i < NWLO; ++i) {
-        ptx::mbar_init(wlo_full(i), 1);
-        ptx::mbar_init(wlo_empty(i), 1);       // tcgen05.commit
-        ptx::mbar_init(wlo_peer(i), 1);        // remote arrive of the peer's forwarder
-      }
-      *s_ready = 0;
-    }
     ptx::fence_mbar_init();
     // resident W2 image(s): this CTA's 128-row half (CG=2) or both halves (CG=1)
     ptx::mbar_expect_tx(bar_wl, S::W_BYTES);
@@ -348,7 +259,7 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
   if (warp == MMA_WARP) ptx::tmem_alloc<CG>(sbase + S::OFF_TMEM, 512);
   pdl_wait();   // row_off, sizes, x, the A|B operands: written by earlier kernels of the chain
   const bool big_b = WIDE && p.B > MAX_B;   // table does not fit the shared-memory slot: searched in global memory
-  if (!big_b) for (int k = tid; k <= p.B; k += NT) s_row[k] = p.row_off[k];
+  if (!big_b) for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();
   ptx::tc_fence_after();
@@ -384,8 +295,7 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
     uint32_t oa[2], ob[2];   // element offsets of A_i / B_j in chunk 0
     bool ok[2];
   };
-  // slab_tile: recv / send are slab slots (64-byte rows of a stage's sub-chunk) and oa / ob become BYTE offsets into it
-  auto read_meta = [&](int t, RowState& r, bool slab_tile = false) {
+  auto read_meta = [&](int t, RowState& r) {
     const PMeta* meta = s_pmeta + (t % PMETA_BUFS) * TILE_M;
 #pragma unroll
     for (int rb = 0; rb < 2; ++rb) {
@@ -393,23 +303,8 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
       r.rr[rb] = m.r;
       r.dd[rb] = m.d0;
       r.ok[rb] = m.recv >= 0;
-      if (slab_tile) {
-        r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 64u + 16u * qsub;
-        r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 64u + 16u * qsub;
-      } else {
-        r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
-        r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
-      }
-    }
-  };
-  // operands of one half step from the slab stage holding its 16-column sub-chunk
-  auto load_slab = [&](float4 (&v)[4], const RowState& r, const uint8_t* sub) {
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb) {
-      if (r.ok[rb]) {
-        v[rb] = *reinterpret_cast<const float4*>(sub + r.oa[rb]);
-        v[2 + rb] = *reinterpret_cast<const float4*>(sub + r.ob[rb]);
-      }
+      r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
+      r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
     }
   };
   auto load_half = [&](float4 (&v)[4], const RowState& r, int hs) {
@@ -564,64 +459,6 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
   // (producing the first tile) then takes about half as long.
   auto produce = [&](int t_begin, int t_end, const bool helper) {
     HD_T0();
-    if constexpr (SLAB) {
-      // Operands come from the slab ring (LDS) - no register prefetch pipeline.  A tile whose distinct operand rows do
-      // not fit a stage (TileInfo::slab == 0) gathers them with plain loads instead.
-      RowState cur;
-      float4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int pending = -1;
-      int gtile = 0;   // slab stages of the slab tiles before tile t
-      for (int t = t_begin; t < t_end; ++t) {
-        if (helper) ptx::mbar_wait(bar_meta0, 0); else ptx::mbar_wait(bar_meta, t & 1);
-        const bool slab_tile = s_tinfo[t % EMETA_BUFS].slab != 0;
-        read_meta(t, cur, slab_tile);
-        __syncwarp();   // this warp holds the tile's metadata in registers: its slot may be recycled
-        if (lane == 0) ptx::mbar_arrive(helper ? bar_hmeta : bar_tstart);
-        HD_ACC(0, 0, tid == 0);
-        const int c_step = (FILL_HELP && t == 0) ? 2 : 1;
-#pragma unroll 1
-        for (int c = (helper && t == 0) ? 1 : 0; c < NCH; c += c_step) {
-          const int gc = t * NCH + c, st = gc % NSTAGE;
-          if (pending == st) {   // (split first tile) this role's previous chunk sits in the very stage it needs next
-            publish(pending);
-            pending = -1;
-          }
-          ptx::mbar_wait(bar_empty(st), ((gc / NSTAGE) & 1) ^ 1);
-          HD_ACC(0, 1, tid == 0);   // wait for a free operand stage
-#pragma unroll
-          for (int hl = 0; hl < HSPS; ++hl) {
-            const int hs = c * HSPS + hl;
-            if (slab_tile) {
-              const int g = gtile + (hs >> 1), slot = g % NSLAB;
-              if ((hs & 1) == 0) ptx::mbar_wait(slab_full(slot), (g / NSLAB) & 1);
-              HD_ACC(0, 5, tid == 0);   // wait for the operand rows
-              load_slab(v, cur, smem + S::OFF_SLAB + slot * SLAB_STAGE + (hs & 1) * SLAB_SUB);
-              half_step(v, cur, hs, st);
-              if (hs & 1) {             // both sub-chunks consumed (their values are in registers): release the stage
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_relaxed(slab_empty(slot));
-              }
-            } else {
-              load_half(v, cur, hs);
-              half_step(v, cur, hs, st);
-            }
-            HD_ACC(0, 2, tid == 0);   // half steps
-            if (hl == 0 && pending >= 0) {
-              publish(pending);
-              pending = -1;
-            }
-            HD_ACC(0, 3, tid == 0);   // publish
-          }
-          pending = st;
-        }
-        if (slab_tile) gtile += SLAB_PER_TILE;
-      }
-      if (pending >= 0) publish(pending);
-      HD_FLUSH(0, tid == 0);
-      return;
-    }
     RowState cur, nxt;
     float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1} of the two half stages in flight
 #pragma unroll
@@ -919,43 +756,6 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
         win_n = p.sizes[wb];
         win_node0 = p.node_off ? p.node_off[wb] : wb * p.N;
       }
-      // SLAB: the molecules this tile touches (lane = molecule), the slab slots of their sender rows and of the
-      // receiver rows that appear in the tile, and whether they all fit one slab stage
-      Seg sg{0, 0, 0, 0, 0, 0};
-      int b_first = 0, senders = 0;
-      bool slab_tile = false;
-      if constexpr (SLAB) {
-        const int tile_lo = row_begin + t * TILE_M, tile_hi = min(tile_lo + TILE_M, row_end);
-        int nseg = 0, rows_used = 0;
-        if (tile_lo < tile_hi) {
-          b_first = find_mol(s_row, p.B, tile_lo);
-          nseg = find_mol(s_row, p.B, tile_hi - 1) - b_first + 1;
-        }
-        if (lane < nseg) {
-          const int mb = b_first + lane, first = s_row[mb], n = p.sizes[mb], npad = (n + 7) & ~7;
-          const int lo = max(tile_lo, first) - first, hi = min(tile_hi, s_row[mb + 1]) - first;   // local rows [lo, hi)
-          sg.node0 = (WIDE && p.node_off) ? p.node_off[mb] : mb * p.N;
-          sg.n = n;
-          sg.i_lo = lo / npad;
-          sg.acnt = (hi - 1) / npad - sg.i_lo + 1;
-        }
-        int pb = sg.n, pa = sg.acnt;   // inclusive scans over the lanes
-#pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-          const int ub = __shfl_up_sync(0xffffffffu, pb, o2), ua = __shfl_up_sync(0xffffffffu, pa, o2);
-          if (lane >= o2) {
-            pb += ub;
-            pa += ua;
-          }
-        }
-        sg.bslot = pb - sg.n;
-        sg.aslot = pa - sg.acnt;
-        senders = __shfl_sync(0xffffffffu, pb, 31);
-        rows_used = senders + __shfl_sync(0xffffffffu, pa, 31);
-        slab_tile = nseg > 0 && nseg <= MAX_SEG && rows_used <= SLAB_SLOTS;
-        if (lane < MAX_SEG) s_seg[(t % EMETA_BUFS) * MAX_SEG + lane] = sg;
-        if (lane == 0) s_tinfo[t % EMETA_BUFS] = TileInfo{nseg, slab_tile ? 1 : 0, rows_used, senders};
-      }
       for (int rq = 0; rq < TILE_M / 32; ++rq) {
         const int row = 32 * rq + lane;
         const int R = row_begin + t * TILE_M + row;
@@ -964,7 +764,6 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
         m.r = m.d0 = e.cd0 = e.cd1 = e.cd2 = 0.f;
         m.recv = m.send = -1;    // row outside this CTA's range
         e.flags = 0;
-        int recv_row = -1, seg_idx = 0, i_of_row = 0, j_of_row = 0;
         int wk = 0, w_first = 0, w_n = 0, w_node0 = 0;
         if (big_b) {             // all lanes take part in the shuffles, in range or not
 #pragma unroll
@@ -999,10 +798,6 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
           const int i = local / npad, j = local - i * npad;
           m.recv = node0 + i;
           m.send = m.recv;
-          recv_row = m.recv;
-          seg_idx = b - b_first;
-          i_of_row = i;
-          j_of_row = j < n ? j : i;   // padding slot: operand row = A_i + B_i (finite, masked later)
           if (j < n) {
             m.send = node0 + j;
             e.flags = 1 | (j == i ? 2 : 0);
@@ -1024,101 +819,22 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
             e.flags = 4;  // padding slot inside a real receiver's group (operand row = A_i + B_i: finite, masked later)
           }
         }
-        if constexpr (SLAB) {   // all lanes take part in the shuffles, in range or not
-          const int sb = __shfl_sync(0xffffffffu, sg.bslot, seg_idx & 31);
-          const int sa = __shfl_sync(0xffffffffu, sg.aslot, seg_idx & 31);
-          const int il = __shfl_sync(0xffffffffu, sg.i_lo, seg_idx & 31);
-          if (slab_tile && recv_row >= 0) {
-            m.send = sb + j_of_row;
-            m.recv = senders + sa + (i_of_row - il);
-          }
-        }
         s_pmeta[(t % PMETA_BUFS) * TILE_M + row] = m;
         s_emeta[(t % EMETA_BUFS) * TILE_M + row] = e;
-        if ((row & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (row >> 3)] = make_int2(recv_row, e.flags != 0);
+        if ((row & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (row >> 3)] = make_int2(m.recv, e.flags != 0);
       }
       __syncwarp();
       if (lane == 0) {
-        if constexpr (SLAB) {   // the copy warp polls this counter (a parity wait could miss a phase: it runs ahead
-          __threadfence_block();                 // of the producers by up to a ring of stages, not in lock step)
-          *s_ready = t + 1;
-        }
         ptx::mbar_arrive(bar_meta);
         if (FILL_HELP && t == 0) ptx::mbar_arrive(bar_meta0);
       }
     }
-  } else if (SLAB && warp == COPY_WARP) {
-    // =========================== operand-row copies (SLAB) ===========================
-    // One bulk copy per touched molecule and 16-column sub-chunk for its sender rows (B image) and one for the receiver
-    // rows that appear in the tile (A image); lane = molecule.  Runs up to NSLAB stages ahead of the producers.
-    int gtile = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      if (lane == 0) {
-        uint32_t spins = 0;
-        while (*s_ready <= t)
-          if (++spins > (1u << 28)) __trap();
-      }
-      __syncwarp();
-      __threadfence_block();
-      const TileInfo ti = s_tinfo[t % EMETA_BUFS];
-      if (!ti.slab) continue;
-      Seg sg{0, 0, 0, 0, 0, 0};
-      if (lane < ti.nseg) sg = s_seg[(t % EMETA_BUFS) * MAX_SEG + lane];
-      const int senders = ti.pad;
-      for (int q = 0; q < SLAB_PER_TILE; ++q) {
-        const int g = gtile + q, slot = g % NSLAB;
-        ptx::mbar_wait(slab_empty(slot), ((g / NSLAB) & 1) ^ 1);
-        if (lane == 0) ptx::mbar_expect_tx(slab_full(slot), 2u * 64u * (uint32_t)ti.rows);
-        if (lane < ti.nseg) {
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int64_t kc = 2 * q + sub;
-            const uint32_t dst = sbase + S::OFF_SLAB + slot * SLAB_STAGE + sub * SLAB_SUB;
-            ptx::bulk_g2s(dst + 64u * sg.bslot, p.b_img + (kc * p.kc_stride + (int64_t)sg.node0 * 16), 64u * sg.n,
-                          slab_full(slot));
-            ptx::bulk_g2s(dst + 64u * (senders + sg.aslot), p.a_img + (kc * p.kc_stride + (int64_t)(sg.node0 + sg.i_lo) * 16),
-                          64u * sg.acnt, slab_full(slot));
-          }
-        }
-        __syncwarp();
-      }
-      gtile += SLAB_PER_TILE;
-    }
-  } else if (SLAB && warp == WLO_WARP) {
-    // =========================== W2 lo stream (SLAB, strict) ===========================
-#ifdef HD_EXP_WLO_ALIAS
-    if (false) {
-#else
-    if (STRICT && lane == 0) {
-#endif
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w_lo) + (size_t)rank * W_HALF;
-      for (int gw = 0; gw < ntiles * SLAB_PER_TILE; ++gw) {
-        const int slot = gw % NWLO;
-        ptx::mbar_wait(wlo_empty(slot), ((gw / NWLO) & 1) ^ 1);
-        ptx::mbar_expect_tx(wlo_full(slot), WLO_CHUNK);
-        ptx::bulk_g2s(sbase + S::OFF_WLO + slot * WLO_CHUNK, src + (size_t)(gw % SLAB_PER_TILE) * WLO_CHUNK, WLO_CHUNK,
-                      wlo_full(slot));
-      }
-    }
-    __syncwarp();
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       ptx::mbar_wait(bar_wl, 0);
       if (CG == 2 && rank != 0) ptx::mbar_arrive_cluster(bar_wr, 0);
       else ptx::mbar_arrive(bar_wr);
-#ifndef HD_EXP_WLO_ALIAS
-      if (SLAB && STRICT && rank != 0) {
-#else
-      if (false) {
-#endif
-        // this CTA issues no MMA: its thread forwards "my chunk of the W2 lo stream has landed" to the issuing CTA
-        for (int gw = 0; gw < ntiles * SLAB_PER_TILE; ++gw) {
-          const int slot = gw % NWLO;
-          ptx::mbar_wait(wlo_full(slot), (gw / NWLO) & 1);
-          ptx::mbar_arrive_cluster(wlo_peer(slot), 0);
-        }
-      }
       if (rank == 0) {
         ptx::mbar_wait(bar_wr, 0);
         constexpr uint32_t IDESC = CG == 2 ? ptx::idesc_bf16(256, 256) : ptx::idesc_bf16(128, 128);
@@ -1144,28 +860,7 @@ __global__ void __launch_bounds__(SLAB ? NTHREADS_SLAB : NTHREADS, 1) edge_tc_k(
                 const uint32_t d = tmem + 256u * as;
                 const uint64_t db_hi = ptx::smem_desc(sbase + S::OFF_W + kgw, W_KG, 128);
                 ptx::mma_bf16<2>(d, da_hi, db_hi, IDESC, acc_on);
-#ifdef HD_EXP_WLO_ALIAS
-                if constexpr (STRICT && SLAB) {
-                  ptx::mma_bf16<2>(d, da_hi, db_hi, IDESC, 1u);
-                  ptx::mma_bf16<2>(d, da_lo, db_hi, IDESC, 1u);
-                } else
-#endif
-                if constexpr (STRICT && SLAB) {
-                  // W2 lo from the stream: 32-column chunk gw (this CTA's and the peer's half must both have landed)
-                  const int gw = gc * (KCH / SLAB_COLS) + (ks >> 1), wslot = gw % NWLO;
-                  if ((ks & 1) == 0) {
-                    HD_ACC(2, 2, true);   // issue
-                    ptx::mbar_wait(wlo_full(wslot), (gw / NWLO) & 1);
-                    HD_ACC(2, 3, true);   // wait for the W2 lo chunk
-                    ptx::mbar_wait(wlo_peer(wslot), (gw / NWLO) & 1);
-                    HD_ACC(2, 4, true);   // ... and for the peer's
-                    ptx::tc_fence_after();
-                  }
-                  const uint64_t db_lo = ptx::smem_desc(sbase + S::OFF_WLO + wslot * WLO_CHUNK + (ks & 1) * 2 * W_KG, W_KG, 128);
-                  ptx::mma_bf16<2>(d, da_hi, db_lo, IDESC, 1u);
-                  ptx::mma_bf16<2>(d, da_lo, db_hi, IDESC, 1u);
-                  if (ks & 1) ptx::mma_commit<CG>(wlo_empty(wslot));   // chunk consumed (both CTAs)
-                } else if constexpr (STRICT) {
+                if constexpr (STRICT) {
                   const uint64_t db_lo = ptx::smem_desc(sbase + S::OFF_W + (S::W_PARTS - 1) * W_HALF + kgw, W_KG, 128);
                   ptx::mma_bf16<2>(d, da_hi, db_lo, IDESC, 1u);
                   ptx::mma_bf16<2>(d, da_lo, db_hi, IDESC, 1u);
@@ -1226,11 +921,11 @@ static int sm_count() {
   return n;
 }
 
-template <bool GCL, bool STRICT, int CG, bool WIDE = false, bool SLAB = false>
+template <bool GCL, bool STRICT, int CG, bool WIDE = false>
 static int launch_edge(const Params& p, cudaStream_t st) {
-  using S = Smem<STRICT, CG, SLAB>;
+  using S = Smem<STRICT, CG>;
   static bool configured = false;
-  auto kern = edge_tc_k<GCL, STRICT, CG, WIDE, SLAB>;
+  auto kern = edge_tc_k<GCL, STRICT, CG, WIDE>;
   if (!configured) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
 #ifdef HD_EXP_CARVEOUT
@@ -1242,7 +937,7 @@ static int launch_edge(const Params& p, cudaStream_t st) {
   int grid = sm_count();
   if (CG == 2) grid &= ~1;
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(SLAB ? NTHREADS_SLAB : NTHREADS);
+  cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1308,27 +1003,6 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   p.norm_div = c.cfg->aggregation_mean ? (float)c.N : c.cfg->normalization_factor;
   const bool strict = engine == HD_ENGINE_TC_STRICT;
   const bool wide = c.B > tc::MAX_B || c.node_off != nullptr;
-  // slab-staged operands (HD_EDGE_SLAB=0 selects the gather kernel): needs the row table in shared memory
-  static const bool slab_on = [] {
-    const char* e = getenv("HD_EDGE_SLAB");
-    return !(e && e[0] == '0');
-  }();
-  if (slab_on && c.B <= tc::MAX_B) {
-    if (!S.is_gcl && !c.x_prezeroed)
-      HD_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 3 * c.B * c.N, c.stream));
-    if (S.is_gcl) {
-      if (wide)
-        return strict ? tc::launch_edge<true, true, 2, true, true>(p, c.stream)
-                      : tc::launch_edge<true, false, 2, true, true>(p, c.stream);
-      return strict ? tc::launch_edge<true, true, 2, false, true>(p, c.stream)
-                    : tc::launch_edge<true, false, 2, false, true>(p, c.stream);
-    }
-    if (wide)
-      return strict ? tc::launch_edge<false, true, 2, true, true>(p, c.stream)
-                    : tc::launch_edge<false, false, 2, true, true>(p, c.stream);
-    return strict ? tc::launch_edge<false, true, 2, false, true>(p, c.stream)
-                  : tc::launch_edge<false, false, 2, false, true>(p, c.stream);
-  }
   if (S.is_gcl) {
     if (wide)
       return strict ? tc::launch_edge<true, true, 2, true>(p, c.stream) : tc::launch_edge<true, false, 2, true>(p, c.stream);

@@ -27,11 +27,7 @@ static void run(const char* name, hd::tc::Params p) {
     cudaMemcpyToSymbol(tc::g_acc, zero, sizeof(zero));
 #endif
     cudaEventRecord(e0);
-#ifdef HD_TIMING_SLAB
-    for (int k = 0; k < 10; ++k) tc::launch_edge<GCL, STRICT, 2, false, true>(p, 0);
-#else
     for (int k = 0; k < 10; ++k) tc::launch_edge<GCL, STRICT, 2>(p, 0);
-#endif
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     cudaEventElapsedTime(&ms, e0, e1);
@@ -50,13 +46,13 @@ static void run(const char* name, hd::tc::Params p) {
   printf("%s: %.2f us/launch; err=%s  (cycles per launch)\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
     const char* pn[] = {"tile prologue+meta", "wait empty stage", "half steps", "publish", "tile barrier", "issue loads"};
   const char* en[] = {"wait accumulator", "pass 1", "dot exchange", "pass 2", "scratch barrier", "combine+release"};
-  const char* mn[] = {"wait free acc", "wait operands", "issue", "wait W2-lo chunk", "wait peer's chunk"};
+  const char* mn[] = {"wait free acc", "wait operands", "issue"};
   long long s = 0;
   for (int i = 0; i < 6; ++i) { printf("  producer  %-20s %8lld\n", pn[i], acc[0][i] / 10); s += acc[0][i] / 10; }
   printf("  producer  total %lld\n", s); s = 0;
   for (int i = 0; i < 6; ++i) { printf("  epilogue  %-20s %8lld\n", en[i], acc[1][i] / 10); s += acc[1][i] / 10; }
   printf("  epilogue  total %lld\n", s); s = 0;
-  for (int i = 0; i < 5; ++i) { printf("  mma       %-20s %8lld\n", mn[i], acc[2][i] / 10); s += acc[2][i] / 10; }
+  for (int i = 0; i < 3; ++i) { printf("  mma       %-20s %8lld\n", mn[i], acc[2][i] / 10); s += acc[2][i] / 10; }
   printf("  mma       total %lld\n", s);
   }
 }
