@@ -259,9 +259,11 @@ __device__ __forceinline__ void block_mean3(const float* v, int N, int D, int n,
 }
 
 // en_dynamics.py:109-116: NaN guard (whole batch) + remove_mean_with_mask; one block per molecule.
+// raw != 0 (HD_ENGINE_RAW_VELOCITY): neither step is applied - the caller combines several node sets first (pocket
+// conditioning) - but a NaN is still reported through `flags`.
 __global__ void __launch_bounds__(128) cog_k(const float* __restrict__ eps_raw, const int32_t* __restrict__ sizes,
                                              int N, int F, const int32_t* __restrict__ nanflag,
-                                             float* __restrict__ eps, int32_t* __restrict__ flags) {
+                                             float* __restrict__ eps, int32_t* __restrict__ flags, int raw) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sv[];  // [N][D]
@@ -269,6 +271,11 @@ __global__ void __launch_bounds__(128) cog_k(const float* __restrict__ eps_raw, 
   const int D = 3 + F, b = blockIdx.x, n = sizes[b];
   const bool nan = *nanflag != 0;
   const float* src = eps_raw + (int64_t)b * N * D;
+  if (raw) {
+    for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) eps[(int64_t)b * N * D + idx] = src[idx];
+    if (nan && flags && b == 0 && threadIdx.x == 0) atomicOr(flags, HD_FLAG_NAN);
+    return;
+  }
   for (int idx = threadIdx.x; idx < N * D; idx += blockDim.x) {
     float v = src[idx];
     if (nan && idx % D < 3) v = 0.f;
@@ -715,17 +722,6 @@ __global__ void final_scalars_k(const float* __restrict__ g0, int count, float* 
   out[3 * k + 2] = expf(-(-0.5f * g));    // SNR(-0.5*gamma_0)
 }
 
-__global__ void loop_fetch_k(int32_t* counter, const float* __restrict__ t_table, const float* __restrict__ sched_table,
-                             int B, int sched_rows, float* __restrict__ t_cur, float* __restrict__ sched_cur) {
-  pdl_wait();
-  pdl_trigger();
-  const int k = *counter;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) t_cur[b] = t_table[k];
-  for (int i = threadIdx.x; i < 3 * sched_rows; i += blockDim.x) sched_cur[i] = sched_table[(int64_t)3 * sched_rows * k + i];
-  __syncthreads();
-  if (threadIdx.x == 0) *counter = k + 1;
-}
-
 // ---------------------------------------------------------------------------------------
 // orchestration
 // ---------------------------------------------------------------------------------------
@@ -853,7 +849,8 @@ HD_API int32_t hd_dynamics_forward_ragged(const hd_config* cfg, const void* pack
   }
   if (live_rows > 0) engine |= HD_ENGINE_RAGGED_ROWS;
   const bool ragged = (engine & HD_ENGINE_RAGGED_ROWS) != 0;
-  engine &= ~HD_ENGINE_RAGGED_ROWS;
+  const int raw = (engine & HD_ENGINE_RAW_VELOCITY) ? 1 : 0;
+  engine &= ~(HD_ENGINE_RAGGED_ROWS | HD_ENGINE_RAW_VELOCITY);
   int rc = check_common(cfg, packed, sizes, B, N, engine);
   if (rc) return rc;
   if (!z || !t || !eps || !workspace) {
@@ -900,7 +897,7 @@ HD_API int32_t hd_dynamics_forward_ragged(const hd_config* cfg, const void* pack
                           nanflag, (const int32_t*)node_off, (int32_t*)nullptr));
   count_launch();
   HD_CHECK_CUDA(launch_pdl(cog_k, dim3(B), dim3(128), sizeof(float) * N * D, c.stream, (const float*)WF(c.W.eps_raw),
-                          sizes, N, F, (const int32_t*)nanflag, eps, flags));
+                          sizes, N, F, (const int32_t*)nanflag, eps, flags, raw));
   count_launch();
   return HD_OK;
 }
@@ -1215,18 +1212,6 @@ HD_API int32_t hd_sampler_final(const hd_config* cfg, const void* packed, const 
     return HD_E_INVALID;
   }
   HD_CHECK_CUDA(launch_pdl(sampler_tail_k<true>, dim3(B), dim3(256), sc.tail_smem, sc.c.stream, sc.a));
-  count_launch();
-  return HD_OK;
-}
-
-HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B,
-                      int32_t sched_rows, float* t_cur, float* sched_cur, hd_stream_t stream) {
-  if (!counter || !t_table || !sched_table || !t_cur || !sched_cur || B < 1 || (sched_rows != 1 && sched_rows != B)) {
-    set_error("bad argument");
-    return HD_E_INVALID;
-  }
-  HD_CHECK_CUDA(launch_pdl(loop_fetch_k, dim3(1), dim3(128), 0, static_cast<cudaStream_t>(stream), counter, t_table,
-                          sched_table, B, sched_rows, t_cur, sched_cur));
   count_launch();
   return HD_OK;
 }

@@ -192,16 +192,24 @@ class DiffusionQM9(nn.Module):
         if fix_noise:
             raise NotImplementedError("fix_noise is not built")
         B, N, _ = zt.shape
-        if mol_shape is not None and mol_shape != N:
-            raise NotImplementedError("pocket conditioning (mol_shape < n_nodes) is not built yet")
         L = native.lib()
-        sizes = self._masks_to_sizes(node_mask, edge_mask)
         gamma_s = self.gamma(s).reshape(-1).float().contiguous()
         gamma_t = self.gamma(t).reshape(-1).float().contiguous()
         sched = torch.empty(B, 3, device=zt.device)
         flags = torch.zeros(1, dtype=torch.int32, device=zt.device)
         zt = zt.contiguous().float()
-        eps = self.dynamics.forward_sizes(t, zt, sizes, flags=flags, context=context)
+        if mol_shape is not None and mol_shape != N:
+            # pocket attached (:321-326): the network sees ligand + pocket, the update touches the ligand only.  Like
+            # the reference, the result holds the ligand rows alone: its ``zt`` is already cut to ``[:, :mol_shape]``
+            # when :345 appends ``zt[:, mol_shape:]`` (an empty slice); ``sample`` re-attaches the pocket every step
+            eps_all = self.phi(zt, t, node_mask, edge_mask, context, mol_shape)
+            N = int(mol_shape)
+            eps = eps_all[:, :N].contiguous()
+            zt = zt[:, :N].contiguous()
+            sizes = sizes_from_node_mask(node_mask.reshape(B, -1)[:, :N], B, N)
+        else:
+            sizes = self._masks_to_sizes(node_mask, edge_mask)
+            eps = self.dynamics.forward_sizes(t, zt, sizes, flags=flags, context=context)
         rx, rh = self._draw(B, N, zt.device)
         zs = torch.empty_like(zt)
         with torch.cuda.device(zt.device):

@@ -50,11 +50,12 @@ class EGNN_dynamics_QM9(nn.Module):
         return self._forward
 
     def forward_sizes(self, t, xh, sizes, flags=None, engine=None, out=None, context=None, ragged=False,
-                      live_rows=0):
+                      live_rows=0, raw=False):
         """``_forward`` with the masks already reduced to ``sizes`` [B] int32 (no validation, no sync).
         ``context`` [B,N,context_node_nf] is appended, unmasked, after the time channel (en_dynamics.py:76-79).
         ``ragged``: performance hint (HD_ENGINE_RAGGED_ROWS) for batches with much padding; same results.
-        ``live_rows``: with ``ragged``, a host-side bound >= sum(sizes) that sizes the node-GEMM grids (0: B*N)."""
+        ``live_rows``: with ``ragged``, a host-side bound >= sum(sizes) that sizes the node-GEMM grids (0: B*N).
+        ``raw``: HD_ENGINE_RAW_VELOCITY - [velocity | h] before the NaN guard and centre-of-gravity projection."""
         native.require_cuda(xh)
         B, N, D = xh.shape
         assert D == self.n_dims + self.in_node_nf - 1, (D, self.in_node_nf)
@@ -75,15 +76,49 @@ class EGNN_dynamics_QM9(nn.Module):
                 egnn.hd_config(), native.ptr(egnn.packed_weights()), native.ptr(xh), native.ptr(t),
                 native.ptr(context), C, native.ptr(sizes), B, N, int(live_rows) if ragged else 0, native.ptr(eps),
                 native.ptr(egnn.workspace(B, N, xh.device)), native.ptr(flags),
-                egnn.engine_id(engine) | (native.ENGINE_RAGGED_ROWS if ragged else 0),
+                egnn.engine_id(engine) | (native.ENGINE_RAGGED_ROWS if ragged else 0)
+                | (native.ENGINE_RAW_VELOCITY if raw else 0),
                 native.stream_ptr()), "hd_dynamics_forward_ragged")
         return eps
+
+    def _forward_pocket(self, t, xh, node_mask, edge_mask, context, mol_shape):
+        """en_dynamics.py:49-122 with ``mol_shape < n_nodes``: the first ``mol_shape`` node slots hold the ligand, the
+        rest the pocket the sampler appended (diffusion_qm9.py:362-371).  Its edge mask is block diagonal (:367-369), so
+        the EGNN stack factorises into a ligand run and a pocket run with the same weights; the pocket coordinates are
+        frozen (:83-88: zero velocity) and both node sets share ONE centre-of-gravity projection (:116)."""
+        B, NT, D = xh.shape
+        N, P = int(mol_shape), NT - int(mol_shape)
+        if context is not None:
+            raise NotImplementedError("context together with a pocket is not built (the reference sampler never does it)")
+        nm = node_mask.reshape(B, NT) != 0
+        em = edge_mask.reshape(B, NT, NT) != 0
+        if bool(em[:, :N, N:].any()) or bool(em[:, N:, :N].any()):
+            raise NotImplementedError("edge_mask must be block diagonal (ligand x ligand, pocket x pocket): the layout "
+                                      "diffusion_qm9.py:367-369 builds")
+        lig_sizes = sizes_from_node_mask(nm[:, :N], B, N)
+        poc_sizes = sizes_from_node_mask(nm[:, N:], B, P)
+        if int(lig_sizes.min()) < 1 or int(poc_sizes.min()) < 1:
+            raise NotImplementedError("every molecule needs at least one ligand node and one pocket node")
+        check_edge_mask(em[:, :N, :N], lig_sizes, B, N)
+        check_edge_mask(em[:, N:, N:], poc_sizes, B, P)
+        flags = torch.zeros(1, dtype=torch.int32, device=xh.device)
+        xh = xh.float()
+        lig = self.forward_sizes(t, xh[:, :N].contiguous(), lig_sizes, flags=flags, raw=True)
+        poc = self.forward_sizes(t, xh[:, N:].contiguous(), poc_sizes, flags=flags, raw=True)
+        vel = torch.cat([lig[..., :3], torch.zeros_like(poc[..., :3])], dim=1)       # :86 pocket coordinates frozen
+        if int(flags.item()) & native.FLAG_NAN:                                      # :109-111 (host sync, as there)
+            print("Warning: detected nan, resetting EGNN output to zero.")
+            vel = torch.zeros_like(vel)
+        nmf = nm.unsqueeze(-1).to(vel.dtype)
+        vel = vel - (vel.sum(1, keepdim=True) / nmf.sum(1, keepdim=True)) * nmf      # models/utils.py:53-56
+        self.last_flags = flags
+        return torch.cat([vel, torch.cat([lig[..., 3:], poc[..., 3:]], dim=1)], dim=2)
 
     def _forward(self, t, xh, node_mask, edge_mask, context, mol_shape=None):
         """en_dynamics.py:49-122."""
         B, N, _ = xh.shape
         if mol_shape is not None and mol_shape != N:
-            raise NotImplementedError("pocket conditioning (mol_shape < n_nodes) is not built yet")
+            return self._forward_pocket(t, xh, node_mask, edge_mask, context, mol_shape)
         sizes = sizes_from_node_mask(node_mask, B, N)
         check_edge_mask(edge_mask, sizes, B, N)
         flags = torch.zeros(1, dtype=torch.int32, device=xh.device)

@@ -13,13 +13,14 @@ ENGINE_FP32 = 0
 ENGINE_TC_STRICT = 1
 ENGINE_TC_FAST = 2
 ENGINE_RAGGED_ROWS = 0x100   # hint bit for hd_dynamics_forward[_ctx]: sum(sizes) << B*N
+ENGINE_RAW_VELOCITY = 0x200  # eps before the NaN guard / centre-of-gravity projection (pocket-conditioned dynamics)
 ENGINES = {"fp32": ENGINE_FP32, "strict": ENGINE_TC_STRICT, "fast": ENGINE_TC_FAST}
 
 FLAG_NAN = 1
 FLAG_COG = 2
 FLAG_MASK = 4
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class HdConfig(ctypes.Structure):
@@ -66,7 +67,6 @@ SIGNATURES = {
     "hd_sampler_step": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
     "hd_sampler_final": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P,
                               _I, _P]),
-    "hd_loop_fetch": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 5
+#define HD_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -50,6 +50,11 @@ extern "C" {
  * below B*N.  The tensor-core engines then keep one workspace row per REAL node (instead of B*N rows), so the
  * per-node GEMMs skip the padding.  Results are bit-identical with and without the hint. */
 #define HD_ENGINE_RAGGED_ROWS 0x100
+/* May be OR-ed into the `engine` argument of hd_dynamics_forward[_ctx|_ragged]: return eps = [velocity | h] BEFORE the
+ * NaN guard and the centre-of-gravity projection of en_dynamics.py:109-116 (a NaN still sets HD_FLAG_NAN).  For callers
+ * that combine several node sets into one projection: pocket-conditioned dynamics (en_dynamics.py:83-88 with
+ * mol_shape < n_nodes), where the ligand and the frozen pocket share one mean. */
+#define HD_ENGINE_RAW_VELOCITY 0x200
 
 /* bits of the device-side status word (`flags`) that kernels OR into */
 #define HD_FLAG_NAN 1       /* en_dynamics.py:109-111 NaN guard fired (velocity zeroed)            */
@@ -168,15 +173,6 @@ HD_API int32_t hd_final_decode(const float* z0, const float* eps0, const float* 
                         int32_t sched_per_mol, float norm_x, float norm_h, float bias_h, float* x,
                         float* h, hd_stream_t stream);
 
-/* Graph-replay helpers for the T-step loop (diffusion_qm9.py:375-384).  A captured step
- * reads its time and schedule scalars through a device-side step counter so ONE captured
- * graph serves all T steps:  hd_loop_fetch copies t_table[*counter] into t_cur[0..B) and row *counter of
- * sched_table [T+1][sched_rows][3] into sched_cur [sched_rows][3], then increments *counter.  sched_rows is B (one
- * row of scalars per molecule, as the reference computes them from its [B,1] gamma calls, diffusion_qm9.py:314-334;
- * pass sched_per_mol = 1 to hd_reverse_step / hd_final_decode) or 1 (one row for the whole batch). */
-HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float* sched_table, int32_t B,
-                      int32_t sched_rows, float* t_cur, float* sched_cur, hd_stream_t stream);
-
 /* The T-step loop of DiffusionQM9.sample (diffusion_qm9.py:361-386) with everything BETWEEN two EGNN stacks in one
  * kernel.  A chain is: hd_sampler_begin, T x hd_sampler_step, hd_sampler_final; the step index lives in `workspace`
  * (reset by _begin, advanced on the device by every _step), so one captured CUDA graph of a step serves all T.
@@ -190,7 +186,7 @@ HD_API int32_t hd_loop_fetch(int32_t* counter, const float* t_table, const float
  *          (diffusion_qm9.py:328-345, as hd_reverse_step, same status bits), step counter, the next forward's input side.
  * _final:  the last forward (t = 0) and sample_p_xh_given_z0 (diffusion_qm9.py:294-310, as hd_final_decode).
  * live_rows / HD_ENGINE_RAGGED_ROWS as hd_dynamics_forward_ragged.  N is limited by the tail kernel's shared memory
- * (3*N*(3+F) floats <= 48 KB). */
+ * ((2*(3+F) + max(3+F, 12)) * N floats <= 48 KB). */
 HD_API int32_t hd_sampler_begin(const hd_config* cfg, const void* packed, const float* z, const float* t_table, int32_t T,
                                 const float* context, int32_t context_nf, const int32_t* sizes, int32_t B, int32_t N,
                                 int32_t live_rows, void* workspace, int32_t* flags, int32_t engine, hd_stream_t stream);

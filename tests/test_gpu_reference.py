@@ -136,6 +136,78 @@ def test_seeded_conditioned_sample_matches_reference(tmp_path):
     assert rel(x.numpy(), x_ref) < 1e-4 and rel(h.numpy(), h_ref) < 1e-4
 
 
+def _pocket_inputs(B, P, seed):
+    g = torch.Generator().manual_seed(seed)
+    n_res = [P, max(P - 2, 1), max(P - 1, 1)][:B] + [P] * max(B - 3, 0)
+    res_type = torch.zeros(B, P, dtype=torch.long)
+    res_pos = torch.zeros(B, P, 3)
+    res_mask = torch.zeros(B, P, 1).bool()
+    res_edge = torch.zeros(B, P, P).bool()
+    for i, n in enumerate(n_res):
+        res_type[i, :n] = torch.randint(1, 21, (n,), generator=g)
+        res_pos[i, :n] = torch.randn(n, 3, generator=g) * 3
+        res_mask[i, :n] = True
+        res_edge[i, :n, :n] = ~torch.eye(n, dtype=torch.bool)
+    return [res_type, res_pos, res_mask, res_edge]
+
+
+def test_pocket_dynamics_forward_matches_reference(tmp_path):
+    """``_forward(..., mol_shape < n_nodes)`` (en_dynamics.py:83-88): ligand + pocket node sets, block-diagonal edge
+    mask, frozen pocket coordinates, one shared centre-of-gravity projection - the FULL output, pocket rows included,
+    against the reference's own ``_forward`` on the same tensors."""
+    from hierdiff_b200.utils import masks_from_sizes
+    sizes, N, P, L = [6, 9, 2], 9, 5, 2
+    ref = R.make_reference(L, 10, pocket=True).to(dev())
+    model = make_model(tmp_path, L, timesteps=10, device=dev(), engine="strict", pocket=True)
+    cond = [c.to(dev()) for c in _pocket_inputs(3, P, seed=4)]
+    B = 3
+    g = torch.Generator().manual_seed(9)
+    nm, em = masks_from_sizes(sizes, N, dev())
+    z = torch.randn(B, N, 11, generator=g).to(dev()) * nm
+    z[..., :3] -= (z[..., :3].sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
+    with torch.no_grad():
+        feat = ref.pocket_embed(cond[0])
+    zt = torch.cat([z, torch.cat([cond[1], feat], dim=-1)], dim=1)
+    node_mask = torch.cat([nm, cond[2]], dim=1)
+    edge_mask = torch.zeros(B, N + P, N + P, dtype=torch.bool, device=dev())
+    edge_mask[:, :N, :N] = em
+    edge_mask[:, N:, N:] = cond[3]
+    t = torch.rand(B, 1, generator=g).to(dev())
+    with torch.no_grad():
+        want = ref.dynamics._forward(t, zt, node_mask, edge_mask, None, N)
+        got = model.dynamics._forward(t, zt, node_mask, edge_mask, None, N)
+    assert got.shape == want.shape == (B, N + P, 11)
+    assert rel(got.cpu().numpy(), want.cpu().numpy()) < 5e-5
+    assert float(got[:, N:, :3].abs().max()) > 0          # the pocket rows carry -mean of the shared projection
+    # one reverse step through the reference's argument list: the ligand rows, updated (the reference returns them alone)
+    s = torch.full((B, 1), 0.3, device=dev())
+    torch.manual_seed(5)
+    with torch.no_grad():
+        zs_ref = ref.sample_p_zs_given_zt(s, s + 0.1, zt.clone(), node_mask, edge_mask, None, mol_shape=N)
+    torch.manual_seed(5)
+    zs = model.sample_p_zs_given_zt(s, s + 0.1, zt.clone(), node_mask, edge_mask, None, mol_shape=N)
+    assert zs.shape == zs_ref.shape == (B, N, 11)
+    assert rel(zs.cpu().numpy(), zs_ref.cpu().numpy()) < 5e-5
+
+
+def test_seeded_pocket_sample_matches_reference(tmp_path):
+    """sample(pocket_cond=...) (diffusion_qm9.py:362-371, :381-382) under a seed vs the reference WITH the pocket
+    attached, same device: the native chain runs the ligand alone (the pocket provably never reaches it)."""
+    sizes, L, T, seed, P = [6, 9, 2], 1, 6, 4, 5
+    cond = _pocket_inputs(3, P, seed=4)
+    ref = R.make_reference(L, T, pocket=True).to(dev())
+    ref.nodes_dist = R.FixedNodes(sizes)
+    torch.manual_seed(seed)
+    res_ref = ref.sample(3, dev(), pocket_cond=[c.to(dev()) for c in cond])
+    model = make_model(tmp_path, L, timesteps=T, device=dev(), engine="strict", pocket=True)
+    model.nodes_dist = R.FixedNodes(sizes)
+    torch.manual_seed(seed)
+    res = model.sample(3, dev(), pocket_cond=cond)
+    for a, b in zip(res, res_ref):
+        assert a["x"].shape == b["x"].shape
+        assert rel(a["x"].numpy(), b["x"].numpy()) < 1e-4 and rel(a["h"].numpy(), b["h"].numpy()) < 1e-4
+
+
 def test_weights_reloaded_after_capture_are_used(tmp_path):
     """sample -> load_state_dict(other weights) -> sample must equal a fresh model with those weights: the packed
     image and the schedule table are rebuilt in place, so the captured graphs read the new values."""
