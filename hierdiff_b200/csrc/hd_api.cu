@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) out_k(const float* __restrict__ h, const 
 }
 
 // prep_k + embed_k in one launch (the sampling path): one CTA per node row.  Block 0 also resets the NaN flag and,
-// for the tensor-core engines, builds the edge-row prefix row_off[b+1] = sum_{b' <= b} n_b' * pad8(n_b') that
+// for the tensor-core engines, builds the edge-row prefix row_off[b+1] = sum_{b' <= b} edge_rows(n_b') that
 // tc::plan_k would otherwise compute in a launch of its own (row_off may be null).
 __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z, const float* __restrict__ t,
                                                     const float* __restrict__ context, int C,
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) prep_embed_k(const float* __restrict__ z,
       for (int base = 0; base < B; base += 32) {
         const int bb = base + tid;
         const int n = bb < B ? sizes[bb] : 0;
-        int v = n * ((n + 7) & ~7);
+        int v = edge_rows(n);
 #pragma unroll
         for (int o2 = 1; o2 < 32; o2 <<= 1) {
           const int u = __shfl_up_sync(0xffffffffu, v, o2);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(256) sampler_begin_k(const SamplerArgs p) {
     for (int base = 0; base < p.B; base += 32) {
       const int bb = base + tid;
       const int nn = bb < p.B ? p.sizes[bb] : 0;
-      int vr = nn * ((nn + 7) & ~7), vn = nn;
+      int vr = edge_rows(nn), vn = nn;
 #pragma unroll
       for (int o2 = 1; o2 < 32; o2 <<= 1) {
         const int ur = __shfl_up_sync(0xffffffffu, vr, o2), un = __shfl_up_sync(0xffffffffu, vn, o2);

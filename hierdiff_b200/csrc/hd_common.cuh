@@ -168,6 +168,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 #endif
 
+// Edge rows of a molecule with n nodes in the tensor-core edge kernel's row space (row_off is its prefix sum):
+// receivers are taken two at a time and, per pair, the rows run over blocks of 8 senders - 8 rows (receiver 2p, senders
+// 8jb..8jb+7) followed by 8 rows (receiver 2p+1, the SAME senders) - so that the two rows an operand-producer thread
+// feeds share their sender and its B_j row is fetched once.  ceil(n/2) pairs x 2 x pad8(n) rows (odd n: the last
+// pair's second half is dead).
+__host__ __device__ inline int edge_rows(int n) { return ((n + 1) >> 1) * 2 * ((n + 7) & ~7); }
+
 // engine entry points (hd_fp32.cu / hd_tc.cu) ------------------------------------------------
 struct FwdCtx {
   const hd_config* cfg;

@@ -145,14 +145,14 @@ __device__ __forceinline__ int find_mol_warp(const int* row_off, int B, int R, i
   }
   return lo;
 }
-// first receiver boundary >= S
+// first receiver-pair boundary >= S (rows of a molecule: hd_common.cuh edge_rows)
 __device__ __forceinline__ int align_recv(const int* row_off, const int32_t* sizes, int B, int S) {
   const int total = row_off[B];
   if (S >= total) return total;
   const int b = find_mol(row_off, B, S);
-  const int n = sizes[b], npad = (n + 7) & ~7;
+  const int n = sizes[b], stride = 2 * ((n + 7) & ~7);
   const int local = S - row_off[b];
-  return row_off[b] + ((local + npad - 1) / npad) * npad;
+  return row_off[b] + ((local + stride - 1) / stride) * stride;
 }
 
 // SiLU in the scaled domain the kernel works in.  Operands arrive as t = -log2(e) * v (the factor is folded into the
@@ -289,10 +289,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   const int rsub = (lane >> 1) & 7;
   const int qsub = 2 * (lane >> 4) + (lane & 1);
   const uint32_t kcs = (uint32_t)p.kc_stride;   // floats between 16-column chunks; b_img = a_img + 16 chunks
-  // per-tile state of the 2 rows this thread feeds (16*pw + 8*rb + rsub); an 8-row group is live or dead as a whole
+  // per-tile state of the 2 rows this thread feeds (16*pw + 8*rb + rsub): receivers 2p and 2p+1 of a pair with the
+  // SAME sender (hd_common.cuh edge_rows), so one B_j load serves both; an 8-row group is live or dead as a whole, and
+  // the second row is never live without the first
   struct RowState {
     float rr[2], dd[2];
-    uint32_t oa[2], ob[2];   // element offsets of A_i / B_j in chunk 0
+    uint32_t oa[2], ob;      // element offsets of A_i (per row) / B_j (shared) in chunk 0
     bool ok[2];
   };
   auto read_meta = [&](int t, RowState& r) {
@@ -304,24 +306,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       r.dd[rb] = m.d0;
       r.ok[rb] = m.recv >= 0;
       r.oa[rb] = (r.ok[rb] ? (uint32_t)m.recv : 0u) * 16u + 4u * qsub;
-      r.ob[rb] = (r.ok[rb] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
+      if (rb == 0) r.ob = (r.ok[0] ? (uint32_t)m.send : 0u) * 16u + 4u * qsub + 16u * kcs;
     }
   };
-  auto load_half = [&](float4 (&v)[4], const RowState& r, int hs) {
+  // v = {A of row 0, A of row 1, B of both}
+  auto load_half = [&](float4 (&v)[3], const RowState& r, int hs) {
     const uint32_t o = hs * kcs;
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb) {
 #ifndef HD_EXP_NO_LDG
-      if (r.ok[rb]) {
-        v[rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[rb])));
-        v[2 + rb] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.ob[rb])));
-      }
-#endif
+    if (r.ok[0]) {
+      v[0] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[0])));
+      v[2] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.ob)));
     }
+    if (r.ok[1]) v[1] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[1])));
+#endif
   };
   // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
   // MUFU latencies of the chains overlap
-  auto half_step = [&](const float4 (&v)[4], const RowState& r, int hs, int s) {
+  auto half_step = [&](const float4 (&v)[3], const RowState& r, int hs, int s) {
     const int ph = hs % HSPS;
     const int k0 = 16 * hs + 4 * qsub;
     const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       const float2 one2 = make_float2(1.0f, 1.0f);
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb) {
-        const float4 a = v[rb], b = v[2 + rb];
+        const float4 a = v[rb], b = v[2];
         const float2 rr2 = make_float2(r.rr[rb], r.rr[rb]), dd2 = make_float2(r.dd[rb], r.dd[rb]);
         q[2 * rb] = ptx::fma2(dd2, make_float2(w_d.x, w_d.y),
                               ptx::fma2(rr2, make_float2(w_r.x, w_r.y), ptx::add2(make_float2(a.x, a.y), make_float2(b.x, b.y))));
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     {
 #pragma unroll
     for (int rb = 0; rb < 2; ++rb) {
-      const float4 a = v[rb], b = v[2 + rb];
+      const float4 a = v[rb], b = v[2];
       pre[4 * rb + 0] = fmaf(r.dd[rb], w_d.x, fmaf(r.rr[rb], w_r.x, a.x + b.x));
       pre[4 * rb + 1] = fmaf(r.dd[rb], w_d.y, fmaf(r.rr[rb], w_r.y, a.y + b.y));
       pre[4 * rb + 2] = fmaf(r.dd[rb], w_d.z, fmaf(r.rr[rb], w_r.z, a.z + b.z));
@@ -460,9 +461,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   auto produce = [&](int t_begin, int t_end, const bool helper) {
     HD_T0();
     RowState cur, nxt;
-    float4 va[4], vb[4];   // {A row0, A row1, B row0, B row1} of the two half stages in flight
+    float4 va[3], vb[3];   // {A row 0, A row 1, B} of the two half stages in flight
 #pragma unroll
-    for (int k = 0; k < 4; ++k) va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 3; ++k) va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto c_first_of = [&](int t) { return (helper && t == 0) ? 1 : 0; };
     auto c_step_of = [&](int t) { return (FILL_HELP && t == 0) ? 2 : 1; };
     auto tile_started = [&]() {   // this warp holds the tile's metadata in registers: its slot may be recycled
@@ -533,14 +534,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16) + 128u * half;
     const float* b2h = s_b2 + 128 * half;
     const float* wah = s_wa + 128 * half;
-    float carry = 0.f;
-    int cur_recv = -1;
+    // running sums of the two receivers of the current pair: even 8-row groups of a tile belong to receiver 2p, odd
+    // groups to receiver 2p+1 (hd_common.cuh edge_rows; tiles start on a 16-row boundary of the pair-aligned range)
+    float carry[2] = {0.f, 0.f};
+    int cur_recv[2] = {-1, -1};
     const float ba = GCL ? p.ba[0] : 0.f;
     if (FILL_HELP && ntiles > 0) produce(0, 1, true);   // pipeline fill: build the odd operand chunks of tile 0
-    auto flush = [&]() {
-      if (cur_recv < 0) return;
-      if (GCL) p.out[(int64_t)cur_recv * H + etid] = (silu_kout<STRICT>() * carry) / p.norm_div;
-      else if (etid < 3) p.out[(int64_t)cur_recv * 3 + etid] = p.x[(int64_t)cur_recv * 3 + etid] + carry / p.norm_div;
+    auto flush = [&](int hh) {
+      const int rcv = cur_recv[hh];
+      if (rcv < 0) return;
+      if (GCL) p.out[(int64_t)rcv * H + etid] = (silu_kout<STRICT>() * carry[hh]) / p.norm_div;
+      else if (etid < 3) p.out[(int64_t)rcv * 3 + etid] = p.x[(int64_t)rcv * 3 + etid] + carry[hh] / p.norm_div;
     };
     HD_T0();
     for (int t = 0; t < ntiles; ++t) {
@@ -706,7 +710,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       ptx::tc_fence_before();
       ptx::named_bar_sync(3, EPI_THREADS);   // scratch complete
       HD_ACC(1, 4, etid == 0);   // scratch barrier
-      // per-receiver running sums: groups of a tile are ordered by receiver; thread = output column
+      // per-receiver running sums: the groups of a receiver are consecutive among those of its parity; thread = output column
       if (GCL || etid < 3) {
         int2 gi[16];
         float sv[16];
@@ -717,13 +721,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         }
 #pragma unroll
         for (int g = 0; g < 16; ++g) {
-          if (!gi[g].y) continue;                 // group outside this CTA's range
-          if (gi[g].x != cur_recv) {
-            flush();
-            cur_recv = gi[g].x;
-            carry = 0.f;
+          if (!gi[g].y) continue;                 // group outside this CTA's range / dead half of an odd pair
+          const int hh = g & 1;
+          if (gi[g].x != cur_recv[hh]) {
+            flush(hh);
+            cur_recv[hh] = gi[g].x;
+            carry[hh] = 0.f;
           }
-          carry += sv[g];
+          carry[hh] += sv[g];
         }
       }
       // accumulator stage drained and this tile's group table no longer needed: hand both back (the producers
@@ -735,7 +740,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       }
       HD_ACC(1, 5, etid == 0);   // combine + release
     }
-    flush();
+    flush(0);
+    flush(1);
     HD_FLUSH(1, etid == 0);
   } else if (warp == META_WARP) {
     // =========================== row metadata ===========================
@@ -793,11 +799,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
             node0 = (WIDE && p.node_off) ? p.node_off[b] : b * p.N;
           }
           (void)b;
+          // rows of a molecule (edge_rows): pair p of receivers, block jb of 8 senders, half hh (receiver 2p + hh)
           const int npad = (n + 7) & ~7;
           const int local = R - first;
-          const int i = local / npad, j = local - i * npad;
+          const int pr = local / (2 * npad), rem = local - pr * 2 * npad;
+          const int i = 2 * pr + ((rem >> 3) & 1), j = ((rem >> 4) << 3) + (rem & 7);
+          if (i < n) {          // else: the dead second half of an odd molecule's last pair
           m.recv = node0 + i;
-          m.send = m.recv;
+          m.send = node0 + 2 * pr;   // padding slot (j >= n): any finite B row, the same for both halves of the pair
           if (j < n) {
             m.send = node0 + j;
             e.flags = 1 | (j == i ? 2 : 0);
@@ -816,7 +825,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
               e.cd2 = d2 / nrm;
             }
           } else {
-            e.flags = 4;  // padding slot inside a real receiver's group (operand row = A_i + B_i: finite, masked later)
+            e.flags = 4;  // padding slot inside a real receiver's group (operand row finite, masked later)
+          }
           }
         }
         s_pmeta[(t % PMETA_BUFS) * TILE_M + row] = m;
@@ -905,7 +915,7 @@ __global__ void plan_k(const int32_t* __restrict__ sizes, int B, int32_t* __rest
   row_off[0] = 0;
   for (int b = 0; b < B; ++b) {
     const int n = sizes[b];
-    acc += n * ((n + 7) & ~7);
+    acc += edge_rows(n);
     row_off[b + 1] = acc;
   }
 }
