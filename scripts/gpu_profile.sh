@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for profiles/ (B200_PROFILING.md recipe): (1) launch list of a short eager chain, (2) --set full
 # captures of the two dominant kernels at the C2 shape.  usage: bash scripts/gpu_profile.sh <engine> <tag>
-E=${1:-strict}; TAG=${2:-r1}
+E=${1:-strict}; TAG=${2:-r2}
 mkdir -p gpurun_out
 echo "== ncu launch list ($E)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \

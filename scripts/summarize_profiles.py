@@ -55,7 +55,9 @@ def launches(engine, tag):
                 seq.append((r[ki], float(r[vi].replace(",", ""))))
             except ValueError:
                 pass
-    idx = [i for i, (k, _) in enumerate(seq) if "reverse_step_k" in k]
+    idx = [i for i, (k, _) in enumerate(seq) if "sampler_tail_k<0>" in k or "sampler_tail_k<false>" in k]
+    if not idx:     # round-1 step structure
+        idx = [i for i, (k, _) in enumerate(seq) if "reverse_step_k" in k]
     if len(idx) < 3:
         return
     win = seq[idx[-3] + 1: idx[-2] + 1]          # one full reverse step, well after warm-up
@@ -67,7 +69,9 @@ def launches(engine, tag):
         f.write(f"# ncu launch list, engine={engine}, one reverse step at C2 (B=64, N=40, L=4)\n\n"
                 "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv python bench.py "
                 f"--engine {engine} --steps 1 --warmup 1 --no-cpu-baseline --no-graph --timesteps 12` "
-                "(scripts/gpu_profile.sh). Per-launch times are serialised and cold-cache: compare shares.\n\n"
+                "(scripts/gpu_profile.sh). Per-launch times are serialised and cold-cache: compare shares.  A step ends "
+                "with the tail kernel (`sampler_tail_k`); the two `distribution_elementwise...` launches are torch's "
+                "`normal_` draws.\n\n"
                 f"Launches in the step: {len(win)}; sum of device time {tot / 1e3:.1f} us.\n\n"
                 "| kernel | launches | sum us | avg us | share |\n|---|---|---|---|---|\n")
         for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
