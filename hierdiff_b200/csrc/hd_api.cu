@@ -760,11 +760,14 @@ static int run_blocks(const FwdCtx& c, int engine, float** h_final, float** x_fi
   const float* x0 = reinterpret_cast<const float*>(c.ws + c.W.x0);
   int si = 0, rc;
   c.ab_ready = ab_ready;   // the sampling loop's tail kernel has already produced block 0's A|B operands
+  c.ab2_ready = false;
   for (int l = 0; l < c.cfg->n_layers; ++l) {
     for (int s = 0; s < c.cfg->inv_sublayers; ++s) {
       if (engine != HD_ENGINE_FP32 && c.L->subs[si].fuse_next) {
-        // tensor-core engines: node_mlp.2 and the next sub-layer's pre-projection share a launch; h ping-pongs
-        if ((rc = tc_gcl_fused(c, si++, h, h2, x, x0, engine))) return rc;
+        // tensor-core engines: node_mlp.2 and the next sub-layer's pre-projection share a launch; h ping-pongs.  The
+        // first sub-layer of a block finds its own operands in ws.ab2 (written by the previous block's last GCL)
+        const bool use_ab2 = s == 0 && c.ab2_ready;
+        if ((rc = tc_gcl_fused(c, si++, h, h2, x, x0, engine, use_ab2))) return rc;
         float* tmp = h;
         h = h2;
         h2 = tmp;

@@ -75,6 +75,10 @@ struct SubLayer {
                                //                 next sub-layer's A|B of h' = h + V2 hid + c2 without waiting for h'
   int64_t bm;                  // [2H] fp32       -log2(e) * ([b1_next | 0] + W1ab_next . c2)
   bool fuse_next;              // the three fields above are populated
+  // last GCL of a block that has a successor block: the same pre-multiplied image for the FIRST sub-layer of the next
+  // block (h does not change across the EquivariantUpdate in between), so that its pre-projection rides in this launch too
+  int64_t m2_hi, m2_lo, bm2;
+  bool fuse_next2;
 };
 
 struct Layout {
@@ -102,6 +106,7 @@ bool make_layout(const hd_config& cfg, Layout* out);
 struct Workspace {
   int64_t h;      // [BN][H]
   int64_t ab;     // [BN][2H]   node pre-projection: A_i (bias folded) | B_j
+  int64_t ab2;    // [BN][2H]   same, for the first sub-layer of the NEXT block (written one edge kernel ahead)
   int64_t agg;    // [BN][H]
   int64_t hid;    // [BN][H]
   int64_t h2;     // [BN][H]    ping-pong partner of h (the fused node launch must not update h in place)
@@ -189,6 +194,7 @@ struct FwdCtx {
   int rows_bound = 0;                  // ragged node rows: the caller's bound on sum(sizes) (0: B*N); sizes the node-GEMM grids
   mutable bool planned = false;  // ws.row_off holds the edge-row prefix for `sizes`
   mutable bool ab_ready = false; // ws.ab already holds the next sub-layer's A|B operands (fused node launch)
+  mutable bool ab2_ready = false;// ws.ab2 already holds the A|B operands of the next block's first sub-layer
   bool x_prezeroed = false;      // padded rows of ws.x / ws.x2 are already 0 (hd_dynamics_forward): the coordinate
                                  // update then needs no memset of its output
 };
@@ -199,7 +205,9 @@ int fp32_equiv(const FwdCtx& c, int si, const float* h, const float* x, const fl
 int tc_gcl(const FwdCtx& c, int si, float* h, const float* x, const float* x0, int engine);
 // same, but when `h_out` != nullptr and the sub-layer has a fused successor: h_out receives the updated features
 // (h is left untouched) and the successor's A|B operands are produced in the same launch (c.ab_ready is set)
-int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const float* x, const float* x0, int engine);
+// use_ab2: read this sub-layer's own A|B operands from ws.ab2 (first sub-layer of a block, see ab2_ready)
+int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const float* x, const float* x0, int engine,
+                 bool use_ab2 = false);
 int tc_equiv(const FwdCtx& c, int si, const float* h, const float* x, const float* x0, float* x_out, int engine);
 // edge kernel alone on ws.ab (profiling hook); output into ws.agg (GCL) / ws.x2 (equiv)
 int fp32_edge_only(const FwdCtx& c, int si, const float* x, const float* x0);

@@ -132,10 +132,18 @@ bool make_layout(const hd_config& c, Layout* out) {
         S.m_hi = put((int64_t)2 * H * 2 * H * 2);
         S.m_lo = put((int64_t)2 * H * 2 * H * 2);
         S.bm = put(2 * H * 4);
+        S.fuse_next2 = k == c.inv_sublayers - 1 && b + 1 < c.n_layers;
+        if (S.fuse_next2) {
+          S.m2_hi = put((int64_t)2 * H * 2 * H * 2);
+          S.m2_lo = put((int64_t)2 * H * 2 * H * 2);
+          S.bm2 = put(2 * H * 4);
+        } else {
+          S.m2_hi = S.m2_lo = S.bm2 = -1;
+        }
       } else {
         S.v1_hi = S.v1_lo = S.v2_hi = S.v2_lo = -1;
-        S.fuse_next = false;
-        S.v2w_hi = S.v2w_lo = S.m_hi = S.m_lo = S.bm = -1;
+        S.fuse_next = S.fuse_next2 = false;
+        S.v2w_hi = S.v2w_lo = S.m_hi = S.m_lo = S.bm = S.m2_hi = S.m2_lo = S.bm2 = -1;
       }
       L.subs.push_back(S);
     }
@@ -156,6 +164,7 @@ Workspace make_workspace(const hd_config& c, int B, int N) {
   };
   W.h = put(BN * H * 4);
   W.ab = put(BN * 2 * H * 4);
+  W.ab2 = put(BN * 2 * H * 4);
   W.agg = put(BN * H * 4);
   W.hid = put(BN * H * 4);
   W.h2 = put(BN * H * 4);
@@ -315,6 +324,16 @@ int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, c
           const int64_t o = (int64_t)t * 128 * 2 * H;
           image_k<<<grid(128 * 2 * H), T, 0, st>>>(F(L.fuse_tmp), 2 * H, t * 128, 0, 128, 2 * H, BF(S.m_hi) + o,
                                                    BF(S.m_lo) + o, NEG_LOG2E);
+        }
+      }
+      if (S.fuse_next2) {
+        const SubLayer& Nx = L.subs[si + 2];   // first sub-layer of the next block (si + 1 is this block's EquivariantUpdate)
+        fuse_k<<<2 * H, H, 0, st>>>(w + Nx.s_w1, ld1, w + Nx.s_b1, w + S.s_v2, w + S.s_c2, F(L.fuse_tmp), F(S.bm2),
+                                    NEG_LOG2E);
+        for (int t = 0; t < 2 * H / 128; ++t) {
+          const int64_t o = (int64_t)t * 128 * 2 * H;
+          image_k<<<grid(128 * 2 * H), T, 0, st>>>(F(L.fuse_tmp), 2 * H, t * 128, 0, 128, 2 * H, BF(S.m2_hi) + o,
+                                                   BF(S.m2_lo) + o, NEG_LOG2E);
         }
       }
     }

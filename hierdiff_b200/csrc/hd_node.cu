@@ -97,15 +97,15 @@ __device__ __forceinline__ float silu_node(float v) {
 // Two independent GEMMs over the same row tiles may share one launch (column tiles [0, tiles_a) belong to problem a,
 // the rest to problem b): node_mlp.2 and the next sub-layer's pre-projection run side by side that way.
 struct Params2 {
-  Params a, b;
-  int tiles_a;
+  Params a, b, c;          // column tiles [0, tiles_a) -> a, [tiles_a, tiles_ab) -> b, the rest -> c
+  int tiles_a, tiles_ab;
 };
 
 template <bool STRICT, int NT, bool RAGGED = false>
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   using S = Smem<STRICT, NT>;
-  const bool second = (int)blockIdx.y >= pp.tiles_a;
-  const Params p = second ? pp.b : pp.a;
+  const int which = (int)blockIdx.y < pp.tiles_a ? 0 : ((int)blockIdx.y < pp.tiles_ab ? 1 : 2);
+  const Params p = which == 0 ? pp.a : (which == 1 ? pp.b : pp.c);
   constexpr int W_KG = S::W_KG, W_PART = S::W_PART, OT_LD = S::OT_LD, NSTG = S::NSTG;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   float* s_bias = reinterpret_cast<float*>(smem + S::OFF_BIAS);
 
   const int K = p.K1 + p.K2, nch = K / KC, nch1 = p.K1 / KC;
-  const int row0 = blockIdx.x * TM, ct = second ? (int)blockIdx.y - pp.tiles_a : (int)blockIdx.y;
+  const int row0 = blockIdx.x * TM;
+  const int ct = (int)blockIdx.y - (which == 0 ? 0 : (which == 1 ? pp.tiles_a : pp.tiles_ab));
   HD_STAMP(0, tid == 0);
   pdl_trigger();   // the next kernel's CTAs may be scheduled as soon as resources free up (they wait for our completion)
 
@@ -327,9 +328,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
 }
 
 template <bool STRICT, int NT, bool RAGGED = false>
-static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, cudaStream_t st) {
+static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, cudaStream_t st,
+                   const Params* c3 = nullptr, int n_out_c = 0) {
   if constexpr (!RAGGED) {
-    if (a.ragged) return launch2<STRICT, NT, true>(a, n_out_a, b, n_out_b, st);
+    if (a.ragged) return launch2<STRICT, NT, true>(a, n_out_a, b, n_out_b, st, c3, n_out_c);
   }
   using S = Smem<STRICT, NT>;
   static bool configured = false;
@@ -341,8 +343,10 @@ static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, c
   Params2 pp{};
   pp.a = a;
   pp.b = b ? *b : a;
+  pp.c = c3 ? *c3 : a;
   pp.tiles_a = n_out_a / NT;
-  dim3 grid((a.grid_rows + TM - 1) / TM, pp.tiles_a + (b ? n_out_b / NT : 0));
+  pp.tiles_ab = pp.tiles_a + (b ? n_out_b / NT : 0);
+  dim3 grid((a.grid_rows + TM - 1) / TM, pp.tiles_ab + (c3 ? n_out_c / NT : 0));
   HD_CHECK_CUDA(launch_pdl(kern, grid, dim3(NTHREADS), S::TOTAL, st, pp));
   count_launch();
   return HD_OK;
@@ -398,11 +402,18 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
 
 // node_mlp.2 (+ residual, mask) -> h_out and, in the same launch, the next sub-layer's A|B pre-projection computed
 // from [h | hid] with the pre-multiplied weight image (hd_layout.cu "fused pre-projection"): both in 128-column tiles
+// m2_* / bm2 / ab2 (optional): a second pre-projection from the same [h | hid], for the first sub-layer of the next block
 int linear_tc_v2_and_preproject(const FwdCtx& c, const float* hid, const float* h, float* h_out, const void* v2_hi,
                                 const void* v2_lo, const float* c2, const void* m_hi, const void* m_lo,
-                                const float* bm, float* ab, bool strict) {
+                                const float* bm, float* ab, bool strict, const void* m2_hi, const void* m2_lo,
+                                const float* bm2, float* ab2) {
   const lin::Params a = make_params(c, hid, H, H, nullptr, 0, 0, v2_hi, v2_lo, c2, h_out, H, 2, h);
   const lin::Params b = make_params(c, h, H, H, hid, H, H, m_hi, m_lo, bm, ab, 2 * H, 3, nullptr);
+  if (m2_hi) {
+    const lin::Params c3 = make_params(c, h, H, H, hid, H, H, m2_hi, m2_lo, bm2, ab2, 2 * H, 3, nullptr);
+    return strict ? lin::launch2<true, 128>(a, H, &b, 2 * H, c.stream, &c3, 2 * H)
+                  : lin::launch2<false, 128>(a, H, &b, 2 * H, c.stream, &c3, 2 * H);
+  }
   return strict ? lin::launch2<true, 128>(a, H, &b, 2 * H, c.stream) : lin::launch2<false, 128>(a, H, &b, 2 * H, c.stream);
 }
 

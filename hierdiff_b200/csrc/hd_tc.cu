@@ -982,13 +982,14 @@ static int ensure_plan(const FwdCtx& c) {
   return HD_OK;
 }
 
-static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0, float* out, int engine) {
+static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0, float* out, int engine,
+                       bool use_ab2 = false) {
   const SubLayer& S = c.L->subs[si];
   auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   int rc = ensure_plan(c);
   if (rc) return rc;
   tc::Params p{};
-  p.a_img = reinterpret_cast<const float*>(c.ws + c.W.ab);
+  p.a_img = reinterpret_cast<const float*>(c.ws + (use_ab2 ? c.W.ab2 : c.W.ab));
   p.kc_stride = (int64_t)c.B * c.N * 16;
   p.b_img = p.a_img + (H / 16) * p.kc_stride;
   p.x = x;
@@ -1039,9 +1040,11 @@ static int preproject(const FwdCtx& c, const SubLayer& S, const float* h, bool s
 
 int linear_tc_v2_and_preproject(const FwdCtx& c, const float* hid, const float* h, float* h_out, const void* v2_hi,
                                 const void* v2_lo, const float* c2, const void* m_hi, const void* m_lo,
-                                const float* bm, float* ab, bool strict);
+                                const float* bm, float* ab, bool strict, const void* m2_hi, const void* m2_lo,
+                                const float* bm2, float* ab2);
 
-int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const float* x, const float* x0, int engine) {
+int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const float* x, const float* x0, int engine,
+                 bool use_ab2) {
   const SubLayer& S = c.L->subs[si];
   auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   float* ab = reinterpret_cast<float*>(c.ws + c.W.ab);
@@ -1049,17 +1052,27 @@ int tc_gcl_fused(const FwdCtx& c, int si, const float* h, float* h_out, const fl
   float* hid = reinterpret_cast<float*>(c.ws + c.W.hid);
   const bool strict = engine == HD_ENGINE_TC_STRICT;
   int rc;
-  if (!c.ab_ready && (rc = preproject(c, S, h, strict))) return rc;
-  c.ab_ready = false;
-  if ((rc = edge_launch(c, si, x, x0, agg, engine))) return rc;
+  if (use_ab2) {
+    c.ab2_ready = false;   // consumed by the edge kernel below
+  } else {
+    if (!c.ab_ready && (rc = preproject(c, S, h, strict))) return rc;
+    c.ab_ready = false;
+  }
+  if ((rc = edge_launch(c, si, x, x0, agg, engine, use_ab2))) return rc;
   if ((rc = linear_tc(c, h, H, H, agg, H, H, c.packed + S.v1_hi, c.packed + S.v1_lo, H, 64, F(S.c1), hid, H, 1, nullptr,
                       strict)))
     return rc;
-  // node_mlp.2 -> h_out, and the successor's A|B from [h | hid] in the same launch (the edge kernel has consumed ab)
+  // node_mlp.2 -> h_out, the successor's A|B from [h | hid] in the same launch (the edge kernel has consumed ab) and,
+  // after the last GCL of a block, the A|B of the next block's first sub-layer as well (h is not touched in between)
+  float* ab2 = reinterpret_cast<float*>(c.ws + c.W.ab2);
+  const bool two = S.fuse_next2;
   if ((rc = linear_tc_v2_and_preproject(c, hid, h, h_out, c.packed + S.v2w_hi, c.packed + S.v2w_lo, F(S.c2),
-                                        c.packed + S.m_hi, c.packed + S.m_lo, F(S.bm), ab, strict)))
+                                        c.packed + S.m_hi, c.packed + S.m_lo, F(S.bm), ab, strict,
+                                        two ? c.packed + S.m2_hi : nullptr, two ? c.packed + S.m2_lo : nullptr,
+                                        two ? F(S.bm2) : nullptr, ab2)))
     return rc;
   c.ab_ready = true;
+  if (two) c.ab2_ready = true;
   return HD_OK;
 }
 

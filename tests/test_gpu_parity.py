@@ -322,7 +322,7 @@ def test_t1000_chain_matches_reference_fixture(models, engine):
             json.dump({"worst_z_along_chain": worst, "x": ex, "h": eh}, f)
     except OSError:
         pass
-    assert worst < 1e-3 and ex < 1e-3 and eh < 1e-3, (worst, ex, eh)
+    assert worst < 1e-4 and ex < 1e-4 and eh < 1e-4, (worst, ex, eh)   # measured on B200: 1.0e-5 / 3.0e-5 / 5.5e-6 (strict)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -111,8 +111,8 @@ def test_seeded_sample_matches_reference_ragged_l9(tmp_path):
 
 def test_seeded_sample_matches_reference_t1000(tmp_path):
     """T=1000 at a small batch (B=2, N=40, L=4: configs[1]'s model and chain length): 1001 forwards, every draw from
-    the shared Philox stream.  Random-init weights make |z| grow along the chain, which amplifies
-    rounding differences; the bound asserted here is the measured one with margin, the measured value is recorded."""
+    the shared Philox stream.  Random-init weights make |z| grow along the chain; measured on B200:
+    9.9e-6 (x), 6.0e-6 (h) - asserted at the 1e-4 of SURVEY.md 8d, the measured value is recorded."""
     sizes, L, T, seed = [40, 40], 4, 1000, 0
     ref = R.make_reference(L, T).to(dev())
     x_ref, h_ref = R.sample_padded(ref, sizes, dev(), seed)
@@ -122,7 +122,7 @@ def test_seeded_sample_matches_reference_t1000(tmp_path):
     ex, eh = rel(x.numpy(), x_ref), rel(h.numpy(), h_ref)
     record("t1000_b2_strict", {"x": ex, "h": eh, "max_abs_x_ref": float(np.abs(x_ref).max())})
     assert np.isfinite(x.numpy()).all()
-    assert ex < 1e-3 and eh < 1e-3, (ex, eh)
+    assert ex < 1e-4 and eh < 1e-4, (ex, eh)
 
 
 def test_seeded_conditioned_sample_matches_reference(tmp_path):
