@@ -42,6 +42,17 @@ __device__ long long g_acc[2][3][16];   // [CTA 10 | CTA 11][role][slot]
 #define HD_FLUSH(role, cond) do { } while (0)
 #endif
 
+// event timeline of one CTA (scripts/edge_timing.cu -DHD_TIMELINE): clock64 stamps, slot -> first time the event happened
+#ifdef HD_TIMELINE
+__device__ long long g_tl[2][128];
+__device__ unsigned long long g_span[160][2];   // globaltimer at entry / exit of every CTA
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define HD_STAMP(slot, cond) do { if ((cond) && (blockIdx.x >> 1) == 5) g_tl[blockIdx.x & 1][slot] = clock64(); \
+    if ((cond) && ((slot) == 0 || (slot) == 4)) g_span[blockIdx.x][(slot) == 4] = gtimer(); } while (0)
+#else
+#define HD_STAMP(slot, cond) do { } while (0)
+#endif
+
 constexpr int TILE_M = 128;           // edge rows per CTA tile
 #ifndef HD_KCH
 #define HD_KCH 64
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   // Everything up to pdl_wait() touches only constants (weights) and on-chip state, so it overlaps the previous
   // kernel's tail: barrier init, the resident W2 image (TMA bulk copies, 64-128 KB), the bias / weight vectors, TMEM.
   pdl_trigger();
+  HD_STAMP(0, tid == 0);
   for (int k = tid; k < H; k += NTHREADS) {
     s_b2[k] = p.b2[k];
     s_wa[k] = p.wa[k];
@@ -260,29 +272,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   pdl_wait();   // row_off, sizes, x, the A|B operands: written by earlier kernels of the chain
   const bool big_b = WIDE && p.B > MAX_B;   // table does not fit the shared-memory slot: searched in global memory
   if (!big_b) for (int k = tid; k <= p.B; k += NTHREADS) s_row[k] = p.row_off[k];
+  // ---- this pair's rows: three lanes find the receiver-pair-aligned boundaries of the two CTAs' ranges -------------
+  // (one search each, side by side; every thread doing all four searches itself cost 2 us of set-up per launch)
+  const int nCTA = gridDim.x;
+  const int* row_tab = big_b ? p.row_off : s_row;
+  int* s_rng = reinterpret_cast<int*>(s_dot);   // [3] boundaries; the dot scratch is not in use yet
+  __syncthreads();                              // s_row complete
+  if (tid < 3) {
+    const int total = row_tab[p.B];
+    const int rpc = (total + nCTA - 1) / nCTA;
+    s_rng[tid] = align_recv(row_tab, p.sizes, p.B, min(((CG == 2 ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x) + tid) * rpc, total));
+  }
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *s_tmem;
-
-  // ---- this CTA's rows ---------------------------------------------------------------------------
-  const int nCTA = gridDim.x;
-  const int* row_tab = big_b ? p.row_off : s_row;
-  const int total = row_tab[p.B];
-  const int rpc = (total + nCTA - 1) / nCTA;
-  auto range_of = [&](int c, int& a, int& e) {
-    a = align_recv(row_tab, p.sizes, p.B, min(c * rpc, total));
-    e = align_recv(row_tab, p.sizes, p.B, min((c + 1) * rpc, total));
-  };
-  int row_begin, row_end;
-  range_of(blockIdx.x, row_begin, row_end);
+  HD_STAMP(1, tid == 0);
+  const int row_begin = s_rng[CG == 2 ? (int)(blockIdx.x & 1u) : 0], row_end = s_rng[(CG == 2 ? (int)(blockIdx.x & 1u) : 0) + 1];
   int ntiles = (row_end - row_begin + TILE_M - 1) / TILE_M;
   if constexpr (CG == 2) {
-    int pa, pe;
-    range_of(blockIdx.x ^ 1, pa, pe);
+    const int pa = s_rng[(blockIdx.x & 1u) ^ 1u], pe = s_rng[((blockIdx.x & 1u) ^ 1u) + 1];
     ntiles = max(ntiles, (pe - pa + TILE_M - 1) / TILE_M);
   }
+  __syncthreads();                              // every thread has read s_rng before the epilogue reuses the slot
 
+  HD_STAMP(2, tid == 0);
   // ---- operand production (the producer warps; for the first tile also the epilogue warps, see below) ----------
   // warp pw builds rows [16 pw, 16 pw + 16) of an operand stage: lane -> (row in 8-group, 4 columns of a 16-column half)
   const int pw = warp < NPW ? warp : warp - NPW;
@@ -312,6 +326,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   // v = {A of row 0, A of row 1, B of both}
   auto load_half = [&](float4 (&v)[3], const RowState& r, int hs) {
     const uint32_t o = hs * kcs;
+#ifdef HD_EXP_HALF_PROD   // timing experiment only (wrong numerics): producers build every other half step
+    if (hs & 1) return;
+#endif
+#ifdef HD_EXP_NO_PROD     // timing experiment only: producers build nothing, only the hand-offs remain
+    return;
+#endif
 #ifndef HD_EXP_NO_LDG
     if (r.ok[0]) {
       v[0] = __ldg(reinterpret_cast<const float4*>(p.a_img + (o + r.oa[0])));
@@ -323,6 +343,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   // one 16-column half stage of this thread's 2 rows: 8 independent SiLU chains, written phase by phase so the
   // MUFU latencies of the chains overlap
   auto half_step = [&](const float4 (&v)[3], const RowState& r, int hs, int s) {
+#ifdef HD_EXP_HALF_PROD
+    if (hs & 1) return;
+#endif
+#ifdef HD_EXP_NO_PROD
+    return;
+#endif
     const int ph = hs % HSPS;
     const int k0 = 16 * hs + 4 * qsub;
     const float4 w_r = *reinterpret_cast<const float4*>(s_wr + k0);
@@ -515,6 +541,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         }
         pending = st;
       }
+      HD_STAMP(16 + t, tid == 0 && t < 16);
       if (t + 1 < t_end) {
         cur = nxt;
         tile_started();
@@ -552,6 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       ptx::mbar_wait(bar_accf(as), (t >> 1) & 1);
       ptx::tc_fence_after();
       HD_ACC(1, 0, etid == 0);   // wait for the accumulator
+      HD_STAMP(32 + t, etid == 0 && t < 16);
       const EMeta mine = s_emeta[(t % EMETA_BUFS) * TILE_M + 32 * q + lane];
       const bool live = (mine.flags & 3) == 1;   // real, off-diagonal edge
       const bool warp_live = __any_sync(0xffffffffu, mine.flags != 0);   // any row of this lane quarter in range
@@ -739,6 +767,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         else ptx::mbar_arrive_relaxed(bar_acce(as));
       }
       HD_ACC(1, 5, etid == 0);   // combine + release
+      HD_STAMP(48 + t, etid == 0 && t < 16);
     }
     flush(0);
     flush(1);
@@ -762,78 +791,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         win_n = p.sizes[wb];
         win_node0 = p.node_off ? p.node_off[wb] : wb * p.N;
       }
-      for (int rq = 0; rq < TILE_M / 32; ++rq) {
-        const int row = 32 * rq + lane;
-        const int R = row_begin + t * TILE_M + row;
-        PMeta m;
-        EMeta e;
-        m.r = m.d0 = e.cd0 = e.cd1 = e.cd2 = 0.f;
-        m.recv = m.send = -1;    // row outside this CTA's range
-        e.flags = 0;
-        int wk = 0, w_first = 0, w_n = 0, w_node0 = 0;
-        if (big_b) {             // all lanes take part in the shuffles, in range or not
+      // the four rows of a lane (32 rq + lane) go through the dependent steps side by side - table search, sizes,
+      // coordinates - so the tile costs one chain of latencies, not four (2.5 us -> < 1 us ahead of the first tile)
+      constexpr int RQ = TILE_M / 32;
+      int Rr[RQ], first[RQ], nn[RQ], node0[RQ];
+#pragma unroll
+      for (int rq = 0; rq < RQ; ++rq) Rr[rq] = row_begin + t * TILE_M + 32 * rq + lane;
+      if (big_b) {             // all lanes take part in the shuffles, in range or not
+#pragma unroll
+        for (int rq = 0; rq < RQ; ++rq) {
+          int wk = 0;
 #pragma unroll
           for (int step = 16; step >= 1; step >>= 1) {
             const int v = __shfl_sync(0xffffffffu, win_first, wk + step);
-            if (v <= R) wk += step;
+            if (v <= Rr[rq]) wk += step;
           }
-          w_first = __shfl_sync(0xffffffffu, win_first, wk);
-          w_n = __shfl_sync(0xffffffffu, win_n, wk);
-          w_node0 = __shfl_sync(0xffffffffu, win_node0, wk);
-          if (rq == TILE_M / 32 - 1) {   // the next tile's window starts at the molecule of this tile's last row
+          first[rq] = __shfl_sync(0xffffffffu, win_first, wk);
+          nn[rq] = __shfl_sync(0xffffffffu, win_n, wk);
+          node0[rq] = __shfl_sync(0xffffffffu, win_node0, wk);
+          if (rq == RQ - 1) {   // the next tile's window starts at the molecule of this tile's last row
             const int last = __shfl_sync(0xffffffffu, wk, 31);
             win_b0 = min(win_b0 + last, p.B - 1);
           }
         }
-        if (R < row_end) {
-          int b, first, n, node0;
-          if (big_b) {
-            b = -1;              // not needed: the window carries first / n / node0
-            first = w_first;
-            n = w_n;
-            node0 = w_node0;
-          } else {
-            b = find_mol(s_row, p.B, R);
-            first = s_row[b];
-            n = p.sizes[b];
-            node0 = (WIDE && p.node_off) ? p.node_off[b] : b * p.N;
-          }
-          (void)b;
-          // rows of a molecule (edge_rows): pair p of receivers, block jb of 8 senders, half hh (receiver 2p + hh)
-          const int npad = (n + 7) & ~7;
-          const int local = R - first;
-          const int pr = local / (2 * npad), rem = local - pr * 2 * npad;
-          const int i = 2 * pr + ((rem >> 3) & 1), j = ((rem >> 4) << 3) + (rem & 7);
-          if (i < n) {          // else: the dead second half of an odd molecule's last pair
-          m.recv = node0 + i;
-          m.send = node0 + 2 * pr;   // padding slot (j >= n): any finite B row, the same for both halves of the pair
-          if (j < n) {
-            m.send = node0 + j;
-            e.flags = 1 | (j == i ? 2 : 0);
-            const float* xi = p.x + 3 * (int64_t)m.recv;
-            const float* xj = p.x + 3 * (int64_t)m.send;
-            const float* oi = p.x0 + 3 * (int64_t)m.recv;
-            const float* oj = p.x0 + 3 * (int64_t)m.send;
-            const float d0 = xi[0] - xj[0], d1 = xi[1] - xj[1], d2 = xi[2] - xj[2];
-            const float e0 = oi[0] - oj[0], e1 = oi[1] - oj[1], e2 = oi[2] - oj[2];
-            m.r = d0 * d0 + d1 * d1 + d2 * d2;
-            m.d0 = e0 * e0 + e1 * e1 + e2 * e2;
-            if (!GCL) {
-              const float nrm = sqrtf(m.r + 1e-8f) + p.norm_constant;
-              e.cd0 = d0 / nrm;
-              e.cd1 = d1 / nrm;
-              e.cd2 = d2 / nrm;
-            }
-          } else {
-            e.flags = 4;  // padding slot inside a real receiver's group (operand row finite, masked later)
-          }
+      } else {
+        // largest b < B with s_row[b] <= R, eight probes (B <= MAX_B = 255); rows past the table end up at B - 1
+        int lo[RQ];
+#pragma unroll
+        for (int rq = 0; rq < RQ; ++rq) lo[rq] = 0;
+#pragma unroll
+        for (int step = 128; step >= 1; step >>= 1) {
+#pragma unroll
+          for (int rq = 0; rq < RQ; ++rq) {
+            const int c = lo[rq] + step;
+            if (c < p.B && s_row[c] <= Rr[rq]) lo[rq] = c;
           }
         }
-        s_pmeta[(t % PMETA_BUFS) * TILE_M + row] = m;
-        s_emeta[(t % EMETA_BUFS) * TILE_M + row] = e;
-        if ((row & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (row >> 3)] = make_int2(m.recv, e.flags != 0);
+#pragma unroll
+        for (int rq = 0; rq < RQ; ++rq) {
+          first[rq] = s_row[lo[rq]];
+          nn[rq] = p.sizes[lo[rq]];
+          node0[rq] = (WIDE && p.node_off) ? p.node_off[lo[rq]] : lo[rq] * p.N;
+        }
+      }
+      // rows of a molecule (edge_rows): pair p of receivers, block jb of 8 senders, half hh (receiver 2p + hh)
+      PMeta pm[RQ];
+      EMeta em[RQ];
+      float xi[RQ][3], xj[RQ][3], oi[RQ][3], oj[RQ][3];
+#pragma unroll
+      for (int rq = 0; rq < RQ; ++rq) {
+        const int n = nn[rq], npad = max((n + 7) & ~7, 8);
+        const int local = max(Rr[rq] - first[rq], 0);
+        const int pr = local / (2 * npad), rem = local - pr * 2 * npad;
+        const int i = 2 * pr + ((rem >> 3) & 1), j = ((rem >> 4) << 3) + (rem & 7);
+        const bool recv_ok = Rr[rq] < row_end && i < n;   // else: outside this CTA's range / the dead second half of an
+                                                           // odd molecule's last pair
+        const bool edge = recv_ok && j < n;
+        pm[rq].recv = recv_ok ? node0[rq] + i : -1;
+        // padding slot (j >= n): any finite B row, the same for both halves of the pair
+        pm[rq].send = recv_ok ? node0[rq] + (edge ? j : 2 * pr) : -1;
+        em[rq].flags = edge ? (1 | (j == i ? 2 : 0)) : (recv_ok ? 4 : 0);   // 4: padding slot inside a real receiver's
+                                                                            // group (operand row finite, masked later)
+        const int64_t ri = edge ? pm[rq].recv : 0, rj = edge ? pm[rq].send : 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          xi[rq][k] = p.x[3 * ri + k];
+          xj[rq][k] = p.x[3 * rj + k];
+          oi[rq][k] = p.x0[3 * ri + k];
+          oj[rq][k] = p.x0[3 * rj + k];
+        }
+      }
+#pragma unroll
+      for (int rq = 0; rq < RQ; ++rq) {
+        const int row = 32 * rq + lane;
+        const bool edge = (em[rq].flags & 1) != 0;
+        const float d0 = xi[rq][0] - xj[rq][0], d1 = xi[rq][1] - xj[rq][1], d2 = xi[rq][2] - xj[rq][2];
+        const float e0 = oi[rq][0] - oj[rq][0], e1 = oi[rq][1] - oj[rq][1], e2 = oi[rq][2] - oj[rq][2];
+        const float r = d0 * d0 + d1 * d1 + d2 * d2;
+        pm[rq].r = edge ? r : 0.f;
+        pm[rq].d0 = edge ? e0 * e0 + e1 * e1 + e2 * e2 : 0.f;
+        em[rq].cd0 = em[rq].cd1 = em[rq].cd2 = 0.f;
+        if (!GCL && edge) {
+          const float nrm = sqrtf(r + 1e-8f) + p.norm_constant;
+          em[rq].cd0 = d0 / nrm;
+          em[rq].cd1 = d1 / nrm;
+          em[rq].cd2 = d2 / nrm;
+        }
+        s_pmeta[(t % PMETA_BUFS) * TILE_M + row] = pm[rq];
+        s_emeta[(t % EMETA_BUFS) * TILE_M + row] = em[rq];
+        if ((row & 7) == 0) s_grp[(t % EMETA_BUFS) * 16 + (row >> 3)] = make_int2(pm[rq].recv, em[rq].flags != 0);
       }
       __syncwarp();
+      HD_STAMP(64 + t, lane == 0 && t < 16);
       if (lane == 0) {
         ptx::mbar_arrive(bar_meta);
         if (FILL_HELP && t == 0) ptx::mbar_arrive(bar_meta0);
@@ -847,6 +896,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
       else ptx::mbar_arrive(bar_wr);
       if (rank == 0) {
         ptx::mbar_wait(bar_wr, 0);
+        HD_STAMP(3, true);
         constexpr uint32_t IDESC = CG == 2 ? ptx::idesc_bf16(256, 256) : ptx::idesc_bf16(128, 128);
         HD_T0();
         for (int t = 0; t < ntiles; ++t) {
@@ -894,6 +944,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
             HD_ACC(2, 2, true);   // issue
           }
           ptx::mma_commit<CG>(bar_accf(as));       // accumulator complete (both CTAs)
+          HD_STAMP(80 + t, t < 16);
         }
         HD_FLUSH(2, true);
       }
@@ -905,6 +956,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_relaxed(); else __syncthreads();   // the peer may still arrive on our barriers
   if (warp == MMA_WARP) ptx::tmem_dealloc<CG>(tmem, 512);
+  HD_STAMP(4, tid == 0);
 }
 
 __global__ void plan_k(const int32_t* __restrict__ sizes, int B, int32_t* __restrict__ row_off) {

@@ -12,7 +12,8 @@ bool pdl_enabled() { return false; }
 int linear_tc(const FwdCtx&, const float*, int, int, const float*, int, int, const void*, const void*, int, int,
               const float*, float*, int, int, const float*, bool) { return 0; }
 int linear_tc_v2_and_preproject(const FwdCtx&, const float*, const float*, float*, const void*, const void*, const float*,
-                                const void*, const void*, const float*, float*, bool) { return 0; }
+                                const void*, const void*, const float*, float*, bool, const void*, const void*,
+                                const float*, float*) { return 0; }
 }
 
 template <bool GCL, bool STRICT>
@@ -38,6 +39,33 @@ static void run(const char* name, hd::tc::Params p) {
 #else
   (void)zero;
   printf("%s: %.2f us/launch; err=%s\n", name, ms * 100.f, cudaGetErrorString(cudaGetLastError()));
+#ifdef HD_TIMELINE
+  {
+    long long tl[2][128];
+    cudaMemcpyFromSymbol(tl, tc::g_tl, sizeof(tl));
+    unsigned long long sp[160][2];
+    cudaMemcpyFromSymbol(sp, tc::g_span, sizeof(sp));
+    unsigned long long e_min = ~0ull, e_max = 0, x_min = ~0ull, x_max = 0;
+    for (int c = 0; c < 148; ++c) {
+      if (sp[c][0] < e_min) e_min = sp[c][0];
+      if (sp[c][0] > e_max) e_max = sp[c][0];
+      if (sp[c][1] < x_min) x_min = sp[c][1];
+      if (sp[c][1] > x_max) x_max = sp[c][1];
+    }
+    printf("  all CTAs (last launch, globaltimer ns): entry spread %llu, first exit %llu, last exit %llu after first entry; CTA 10: entry +%llu exit +%llu\n",
+           e_max - e_min, x_min - e_min, x_max - e_min, sp[10][0] - e_min, sp[10][1] - e_min);
+    for (int c = 0; c < 148; c += 2) printf("%s%llu-%llu", c ? " " : "   ", (sp[c][0] - e_min) / 100, (sp[c][1] - e_min) / 100);
+    printf("\n");
+    for (int cta = 0; cta < 2; ++cta) {
+      const long long t0 = tl[cta][0];
+      auto us = [&](int s) { return (tl[cta][s] - t0) / 1965.0; };
+      printf("  rank %d: setup done %.2f | ranges %.2f | W ready %.2f | exit %.2f (us after entry)\n", cta, us(1), us(2), us(3), us(4));
+      for (int t = 0; t < 8; ++t)
+        printf("    tile %d: meta %.2f | produced %.2f | mma issued %.2f | acc seen %.2f | epilogue done %.2f\n", t, us(64 + t),
+               us(16 + t), us(80 + t), us(32 + t), us(48 + t));
+    }
+  }
+#endif
   return;
 #endif
   for (int cta = 0; cta < 2; ++cta) {

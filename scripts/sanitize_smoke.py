@@ -1,5 +1,5 @@
 import sys, os, tempfile, numpy as np, torch
-ROOT='/root/repo'
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, ROOT+'/tests', ROOT+'/tests/golden'): sys.path.insert(0,p)
 from helpers import make_model, random_batch
 dev=torch.device('cuda',0)
@@ -21,5 +21,11 @@ with tempfile.TemporaryDirectory() as tmp:
             for ragged in (False,True):
                 eps=model.dynamics.forward_sizes(torch.from_numpy(t).to(dev),torch.from_numpy(z).to(dev),torch.from_numpy(sizes).to(dev),ragged=ragged)
                 torch.cuda.synchronize(); print(eng,B,N,'ragged' if ragged else 'padded',float(eps.abs().max()))
-    model.engine='strict'
-    torch.manual_seed(0); print(len(model.sample(3,dev)))
+    # the sampling loop (begin / step / final: tail kernel, loop state), eager and graph, padded and ragged rows
+    for eng in ('strict','fp32'):
+        model.engine=eng
+        for graph in (False, True):
+            model.use_cuda_graph=graph; model._loops={}
+            torch.manual_seed(0); print(eng, 'graph' if graph else 'eager', len(model.sample(3,dev)))
+    model.engine='strict'; model._loops={}
+    x,h=model.sample_padded([3]*99+[40], dev); print('ragged chain', tuple(x.shape), float(x.abs().max()))
