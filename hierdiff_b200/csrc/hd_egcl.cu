@@ -1,0 +1,441 @@
+// hd_egcl.cu - the stage-2 equivariant layer E_GCL (reference ROOT models/egnn/gcl.py:9-209, as built by
+// models/edge_denoise.py:35-43) on the dense edge list of edge_denoise.py:506-524: SURVEY.md 8f-3, first correct CUDA
+// path (fp32 CUDA-core arithmetic; not yet on the tensor cores).
+//
+// Unlike the coarse-grained GCL, an edge carries a feature VECTOR (edges_in_d = hidden_nf for gcl_full_*), the messages
+// are aggregated over `col` (gcl.py:121), and the layer also updates the edge features (edge_model :109-115).  The first
+// Linear of mes_mlp is split per input block, W1 . [h_row, h_col, radial, e] = A_row + B_col + radial * w_r + We . e, so
+// the [E, 2H+1+De] concatenation of gcl.py:93-97 never exists; the same for edge_mlp.0 on [m, radial, e].
+//
+// Two edge sources: the dense list (row = col = null: every (b, i, j) of B molecules padded to N nodes, masks from
+// `sizes`; gcl_full_* of sample_AR, edge_denoise.py:293-294) with a deterministic per-column reduction, and an explicit
+// (row, col) list with optional per-edge / per-node float masks (gcl_focal_* / gcl_edge / gcl_denoise on the search
+// edges, edge_denoise.py:309-310, :347, :398) reduced with atomics.
+//
+//   gemm_k         Y = epilogue([X1 | X2] . W^T + bias + s * w_s): 64x64 tiles, fp32 FFMA, nn.Linear layout [out][in]
+//   mes1_k         m1 = SiLU(A_row + B_col + radial * w_r + P)                             (gcl.py:98, first layer)
+//   att_k          m = m2 * sigmoid(m2 . wa + ba) * edge_mask                              (:100-106)
+//   node_reduce_k  dense: agg_j = sum_i m_ij (:121); x_j' = (x_j + sum_i coord_diff_ij * tanh(c1_ij . wc) * range
+//                  * mask) * node_mask (:131-154, :193-194)
+//   scatter_k / x_finish_k   the same for an explicit list (atomicAdd into zeroed accumulators)
+#include "hd_common.cuh"
+
+namespace hd {
+namespace egcl {
+
+struct Offsets {   // float offsets into the flat state_dict-order parameter buffer (-1: absent)
+  int64_t mes0_w, mes0_b, mes2_w, mes2_b, edge0_w, edge0_b, edge2_w, edge2_b, node0_w, node0_b, node2_w, node2_b,
+      coord0_w, coord0_b, coord2_w, att_w, att_b, total;
+};
+
+static Offsets offsets(const hd_egcl_config& c) {
+  Offsets o{};
+  const int64_t Hh = c.hidden_nf, De = c.edges_in_d;
+  int64_t s = 0;
+  auto take = [&](int64_t n) { int64_t r = s; s += n; return r; };
+  o.mes0_w = take(Hh * (2 * Hh + 1 + De)); o.mes0_b = take(Hh);
+  o.mes2_w = take(Hh * Hh); o.mes2_b = take(Hh);
+  if (c.edge_update) {
+    o.edge0_w = take(Hh * (Hh + 1 + De)); o.edge0_b = take(Hh);
+    o.edge2_w = take(Hh * Hh); o.edge2_b = take(Hh);
+  } else {
+    o.edge0_w = o.edge0_b = o.edge2_w = o.edge2_b = -1;
+  }
+  o.node0_w = take(Hh * 2 * Hh); o.node0_b = take(Hh);
+  o.node2_w = take(Hh * Hh); o.node2_b = take(Hh);
+  o.coord0_w = take(Hh * Hh); o.coord0_b = take(Hh);
+  o.coord2_w = take(Hh);
+  if (c.attention) { o.att_w = take(Hh); o.att_b = take(1); } else { o.att_w = o.att_b = -1; }
+  o.total = s;
+  return o;
+}
+
+struct Work {   // byte offsets, 256-aligned
+  int64_t ab, p, m1, m, c1, agg, hid, e1, radial, xacc, total;
+};
+static Work work(const hd_egcl_config& c, int64_t n_nodes, int64_t E) {
+  Work w{};
+  const int64_t Hh = c.hidden_nf;
+  int64_t p = 0;
+  auto put = [&](int64_t bytes) { int64_t r = p; p = (p + bytes + 255) & ~int64_t(255); return r; };
+  w.ab = put(n_nodes * 2 * Hh * 4);
+  w.p = put(E * Hh * 4);
+  w.m1 = put(E * Hh * 4);
+  w.m = put(E * Hh * 4);
+  w.c1 = put(E * Hh * 4);
+  w.agg = put(n_nodes * Hh * 4);
+  w.hid = put(n_nodes * Hh * 4);
+  w.e1 = put(c.edge_update ? E * Hh * 4 : 0);
+  w.radial = put(E * 4);
+  w.xacc = put(n_nodes * 3 * 4);
+  w.total = p;
+  return w;
+}
+
+// Where the edges come from.  Dense (row == null): edge e = (b, i, j), row = b*N + i, col = b*N + j, live iff
+// i, j < n_b and i != j (the prefix node masks / off-diagonal edge masks of the sampler's batches).  Explicit list:
+// row[e], col[e], multiplier emask[e] (null: 1).
+struct EdgeSrc {
+  const int32_t *row, *col;
+  const float* emask;
+  const int32_t* sizes;
+  int N;
+};
+__device__ __forceinline__ float edge_get(const EdgeSrc& s, int64_t e, int& row, int& col) {
+  if (s.row) {
+    row = s.row[e];
+    col = s.col[e];
+    return s.emask ? s.emask[e] : 1.f;
+  }
+  const int j = (int)(e % s.N);
+  const int64_t r = e / s.N;
+  const int i = (int)(r % s.N), b = (int)(r / s.N);
+  row = b * s.N + i;
+  col = b * s.N + j;
+  const int n = s.sizes[b];
+  return (i < n && j < n && i != j) ? 1.f : 0.f;
+}
+// node mask of row m: dense = prefix mask from sizes; list = nmask[m] (null: 1)
+struct NodeSrc {
+  const float* nmask;
+  const int32_t* sizes;
+  int N;
+};
+__device__ __forceinline__ float node_get(const NodeSrc& s, int m) {
+  if (s.sizes) return (m % s.N) < s.sizes[m / s.N] ? 1.f : 0.f;
+  return s.nmask ? s.nmask[m] : 1.f;
+}
+
+// Y[M, Nout] = act([X1 | X2] . W^T + bias + s[m] * ws) (+ resid) (* rowmask), W = nn.Linear weight [Nout][ldw] whose columns
+// [c1, c1+K1) multiply X1 and [c2, c2+K2) multiply X2, ws = column cs of W (rank-1 term, s may be null).
+struct GemmArgs {
+  const float *X1, *X2, *W, *bias, *s, *resid;
+  float* Y;
+  int M, Nout, K1, K2, ld1, ld2, ldw, c1, c2, cs, ldy, act;   // act: 0 none, 1 SiLU
+  int mask_mode;          // 0 none, 1 node rows (NodeSrc), 2 edge rows (EdgeSrc, applied twice: gcl.py:113-115, :196-197)
+  int mask_twice;
+  EdgeSrc es;
+  NodeSrc ns;
+};
+
+__global__ void __launch_bounds__(256) gemm_k(const GemmArgs a) {
+  __shared__ float sx[16][64 + 1], sw[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  const int K = a.K1 + a.K2;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+      const int r = idx >> 4, k = (idx & 15) + k0;
+      float xv = 0.f, wv = 0.f;
+      if (k < K) {
+        const int m = m0 + r, n = n0 + r;
+        if (m < a.M) xv = k < a.K1 ? a.X1[(int64_t)m * a.ld1 + k] : a.X2[(int64_t)m * a.ld2 + (k - a.K1)];
+        if (n < a.Nout) wv = a.W[(int64_t)n * a.ldw + (k < a.K1 ? a.c1 + k : a.c2 + (k - a.K1))];
+      }
+      sx[idx & 15][r] = xv;
+      sw[idx & 15][r] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float xr[4], wr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xr[i] = sx[k][ty * 4 + i];
+        wr[i] = sw[k][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+    float mk = 1.f;
+    if (a.mask_mode == 1) mk = node_get(a.ns, m);
+    if (a.mask_mode == 2) {
+      int row, col;
+      mk = edge_get(a.es, m, row, col);
+      if (a.mask_twice) mk *= mk;
+    }
+    const float sv = a.s ? a.s[m] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.Nout) continue;
+      float v = acc[i][j];
+      if (a.bias) v += a.bias[n];
+      if (a.s) v = fmaf(sv, a.W[(int64_t)n * a.ldw + a.cs], v);
+      if (a.act == 1) v = silu_acc(v);
+      if (a.resid) v += a.resid[(int64_t)m * a.ldy + n];
+      a.Y[(int64_t)m * a.ldy + n] = a.mask_mode ? v * mk : v;
+    }
+  }
+}
+
+// per edge: radial, m1 = SiLU(A_row + B_col + radial * w_r + (P or sum_d e_d * w_e,d))     one CTA of 128 threads per edge
+__global__ void mes1_k(const float* __restrict__ ab, const float* __restrict__ pe, const float* __restrict__ edge_attr,
+                       int De, const float* __restrict__ x, const float* __restrict__ w0, int ldw, int col_r,
+                       const EdgeSrc es, int Hh, float* __restrict__ radial, float* __restrict__ m1) {
+  const int64_t e = blockIdx.x;
+  int row, col;
+  edge_get(es, e, row, col);
+  const float d0 = x[row * 3] - x[col * 3], d1 = x[row * 3 + 1] - x[col * 3 + 1], d2 = x[row * 3 + 2] - x[col * 3 + 2];
+  const float r = d0 * d0 + d1 * d1 + d2 * d2;
+  if (threadIdx.x == 0) radial[e] = r;
+  for (int k = threadIdx.x; k < Hh; k += blockDim.x) {
+    float v = ab[(int64_t)row * 2 * Hh + k] + ab[(int64_t)col * 2 * Hh + Hh + k];
+    v = fmaf(r, w0[(int64_t)k * ldw + col_r], v);
+    if (pe) {
+      v += pe[e * Hh + k];
+    } else {
+      for (int d = 0; d < De; ++d) v = fmaf(edge_attr[e * De + d], w0[(int64_t)k * ldw + col_r + 1 + d], v);
+    }
+    m1[e * Hh + k] = silu_acc(v);
+  }
+}
+
+// per edge (one warp): m = m2 * sigmoid(m2 . wa + ba) * edge_mask   (attention == 0: only the mask)
+__global__ void att_k(float* __restrict__ m, const float* __restrict__ wa, const float* __restrict__ ba, int attention,
+                      const EdgeSrc es, int Hh, int64_t E) {
+  const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  int row, col;
+  const float mk = edge_get(es, e, row, col);
+  float att = 1.f;
+  if (attention) {
+    float dot = 0.f;
+    for (int k = lane; k < Hh; k += 32) dot = fmaf(m[e * Hh + k], wa[k], dot);
+    dot = warp_sum(dot);
+    att = sigmoid_acc(dot + ba[0]);
+  }
+  const float sc = att * mk;
+  if (!attention && mk == 1.f) return;
+  for (int k = lane; k < Hh; k += 32) m[e * Hh + k] *= sc;
+}
+
+__device__ __forceinline__ float trans_scale(float phi, int use_tanh, float range) {
+  return use_tanh ? tanhf(phi) * range : phi;
+}
+
+// dense list, per node j (one CTA): agg_j = sum_i m_ij ; x_j' = (x_j + sum_i trans_ij) * node_mask
+__global__ void node_reduce_k(const float* __restrict__ m, const float* __restrict__ c1, const float* __restrict__ wc,
+                              const float* __restrict__ x, const int32_t* __restrict__ sizes, int N, int Hh, int use_tanh,
+                              float range, float* __restrict__ agg, float* __restrict__ x_out) {
+  extern __shared__ float s_phi[];   // [N]
+  const int node = blockIdx.x, b = node / N, j = node % N, n = sizes[b], tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  // phi_ij = c1_ij . wc for every sender i of this column (a warp per edge)
+  for (int i = warp; i < N; i += nwarp) {
+    const int64_t e = ((int64_t)b * N + i) * N + j;
+    float dot = 0.f;
+    for (int k = lane; k < Hh; k += 32) dot = fmaf(c1[e * Hh + k], wc[k], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) s_phi[i] = dot;
+  }
+  __syncthreads();
+  for (int k = tid; k < Hh; k += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < N; ++i) s += m[(((int64_t)b * N + i) * N + j) * Hh + k];   // masked edges contribute 0
+    agg[(int64_t)node * Hh + k] = s;
+  }
+  if (tid < 3) {
+    float s = 0.f;
+    const float xj = x[node * 3 + tid];
+    for (int i = 0; i < N; ++i) {
+      if (!(i < n && j < n && i != j)) continue;
+      const int row = b * N + i;
+      const float d0 = x[row * 3] - x[node * 3], d1 = x[row * 3 + 1] - x[node * 3 + 1], d2 = x[row * 3 + 2] - x[node * 3 + 2];
+      const float nrm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2 + 1e-8f) + 1.0f;                 // gcl.py:205-207
+      const float cd = (tid == 0 ? d0 : (tid == 1 ? d1 : d2)) / nrm;
+      s += cd * trans_scale(s_phi[i], use_tanh, range);
+    }
+    x_out[node * 3 + tid] = (xj + s) * (j < n ? 1.f : 0.f);
+  }
+}
+
+// explicit list, per edge (one warp): agg[col] += m_e ; xacc[col] += coord_diff_e * tanh(c1_e . wc) * range * mask
+__global__ void scatter_k(const float* __restrict__ m, const float* __restrict__ c1, const float* __restrict__ wc,
+                          const float* __restrict__ x, const EdgeSrc es, int Hh, int use_tanh, float range, int64_t E,
+                          float* __restrict__ agg, float* __restrict__ xacc) {
+  const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  int row, col;
+  const float mk = edge_get(es, e, row, col);
+  float dot = 0.f;
+  for (int k = lane; k < Hh; k += 32) {
+    dot = fmaf(c1[e * Hh + k], wc[k], dot);
+    atomicAdd(&agg[(int64_t)col * Hh + k], m[e * Hh + k]);
+  }
+  dot = warp_sum(dot);
+  if (lane < 3) {
+    const float d0 = x[row * 3] - x[col * 3], d1 = x[row * 3 + 1] - x[col * 3 + 1], d2 = x[row * 3 + 2] - x[col * 3 + 2];
+    const float nrm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2 + 1e-8f) + 1.0f;
+    const float cd = (lane == 0 ? d0 : (lane == 1 ? d1 : d2)) / nrm;
+    atomicAdd(&xacc[col * 3 + lane], cd * trans_scale(dot, use_tanh, range) * mk);
+  }
+}
+__global__ void x_finish_k(const float* __restrict__ x, const float* __restrict__ xacc, const NodeSrc ns, int count,
+                           float* __restrict__ x_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < count) x_out[idx] = (x[idx] + xacc[idx]) * node_get(ns, idx / 3);
+}
+
+static int gemm(cudaStream_t st, const GemmArgs& a) {
+  if (a.M < 1) return HD_OK;
+  dim3 grid((a.M + 63) / 64, (a.Nout + 63) / 64);
+  gemm_k<<<grid, 256, 0, st>>>(a);
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+}  // namespace egcl
+}  // namespace hd
+
+using namespace hd;
+
+extern "C" {
+
+HD_API int64_t hd_egcl_weight_count(const hd_egcl_config* cfg) {
+  if (!cfg || cfg->hidden_nf < 1 || cfg->edges_in_d < 1) return HD_E_INVALID;
+  return egcl::offsets(*cfg).total;
+}
+
+HD_API int64_t hd_egcl_workspace_bytes(const hd_egcl_config* cfg, int64_t n_nodes, int64_t n_edges) {
+  if (!cfg || n_nodes < 1 || n_edges < 0) return HD_E_INVALID;
+  return egcl::work(*cfg, n_nodes, n_edges).total;
+}
+
+HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const float* h, const float* x,
+                               const float* edge_attr, const int32_t* row, const int32_t* col, const float* edge_mask,
+                               const float* node_mask, const int32_t* sizes, int32_t B, int32_t N, int64_t n_nodes,
+                               int64_t n_edges, float* h_out, float* x_out, float* edge_out, void* workspace,
+                               hd_stream_t stream) {
+  if (!cfg || !w || !h || !x || !h_out || !x_out || !workspace) {
+    set_error("null argument");
+    return HD_E_INVALID;
+  }
+  const bool dense = row == nullptr && (col != nullptr || sizes != nullptr || n_edges != 0);   // an EMPTY list has no row either
+  if (dense) {
+    if (col || !sizes || B < 1 || N < 1 || N > 1024) {
+      set_error("dense edge list needs sizes, B >= 1, 1 <= N <= 1024 and no col");
+      return HD_E_INVALID;
+    }
+    n_nodes = (int64_t)B * N;
+    n_edges = n_nodes * N;
+  } else if ((n_edges > 0 && (!row || !col)) || n_nodes < 1 || n_edges < 0) {
+    set_error("explicit edge list needs row, col, n_nodes >= 1, n_edges >= 0");
+    return HD_E_INVALID;
+  }
+  if (n_edges > 0 && (!edge_attr || (cfg->edge_update && !edge_out))) {
+    set_error("null edge_attr / edge_out");
+    return HD_E_INVALID;
+  }
+  if (cfg->hidden_nf < 32 || cfg->hidden_nf > 1024 || cfg->edges_in_d < 1) {
+    set_error("unsupported shape hidden_nf=%d edges_in_d=%d", cfg->hidden_nf, cfg->edges_in_d);
+    return HD_E_INVALID;
+  }
+  if (n_edges > 0x7fffffff / 4 || n_nodes > 0x7fffffff / 4) {
+    set_error("too many edges (%lld) or nodes (%lld)", (long long)n_edges, (long long)n_nodes);
+    return HD_E_INVALID;
+  }
+  const egcl::Offsets o = egcl::offsets(*cfg);
+  const egcl::Work W = egcl::work(*cfg, n_nodes, n_edges);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  auto WF = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int Hh = cfg->hidden_nf, De = cfg->edges_in_d;
+  const int BN = (int)n_nodes, E = (int)n_edges;
+  const egcl::EdgeSrc es{row, col, edge_mask, dense ? sizes : nullptr, N};
+  const egcl::NodeSrc ns{node_mask, dense ? sizes : nullptr, N};
+  const bool has_emask = dense || edge_mask != nullptr;
+  const bool has_nmask = dense || node_mask != nullptr;
+  float* radial = WF(W.radial);
+  const int ld_mes = 2 * Hh + 1 + De, ld_edge = Hh + 1 + De;
+  int rc;
+  // 1. A|B = h . [W1[:, :H] | W1[:, H:2H]]^T (+ b1 on the A half): two GEMMs on the node rows
+  egcl::GemmArgs g{};
+  g.X1 = h; g.X2 = h; g.K1 = Hh; g.K2 = 0; g.ld1 = Hh; g.ld2 = Hh; g.W = w + o.mes0_w; g.ldw = ld_mes; g.M = BN; g.Nout = Hh;
+  g.ldy = 2 * Hh;
+  g.c1 = 0; g.bias = w + o.mes0_b; g.Y = WF(W.ab);
+  if ((rc = egcl::gemm(st, g))) return rc;
+  g.c1 = Hh; g.bias = nullptr; g.Y = WF(W.ab) + Hh;
+  if ((rc = egcl::gemm(st, g))) return rc;
+  if (E > 0) {
+    // 2. P = edge_attr . W1[:, 2H+1:]^T on the edge rows (narrow edge features are folded into mes1_k instead)
+    const bool use_p = De > 8;
+    if (use_p) {
+      g = egcl::GemmArgs{};
+      g.X1 = edge_attr; g.X2 = edge_attr; g.K1 = De; g.ld1 = De; g.ld2 = De; g.W = w + o.mes0_w; g.ldw = ld_mes; g.c1 = 2 * Hh + 1;
+      g.M = E; g.Nout = Hh; g.ldy = Hh; g.Y = WF(W.p);
+      if ((rc = egcl::gemm(st, g))) return rc;
+    }
+    // 3. m1 = SiLU(A_row + B_col + radial * w_r + P)
+    egcl::mes1_k<<<E, 128, 0, st>>>(WF(W.ab), use_p ? WF(W.p) : nullptr, edge_attr, De, x, w + o.mes0_w, ld_mes, 2 * Hh, es,
+                                    Hh, radial, WF(W.m1));
+    HD_CHECK_LAUNCH();
+    // 4. m2 = SiLU(m1 . W2^T + b2)
+    g = egcl::GemmArgs{};
+    g.X1 = WF(W.m1); g.X2 = g.X1; g.K1 = Hh; g.ld1 = Hh; g.ld2 = Hh; g.W = w + o.mes2_w; g.ldw = Hh; g.bias = w + o.mes2_b;
+    g.M = E; g.Nout = Hh; g.ldy = Hh; g.Y = WF(W.m); g.act = 1;
+    if ((rc = egcl::gemm(st, g))) return rc;
+    // 5. attention gate and edge mask
+    if (cfg->attention || has_emask) {
+      egcl::att_k<<<(E + 7) / 8, 256, 0, st>>>(WF(W.m), cfg->attention ? w + o.att_w : nullptr,
+                                           cfg->attention ? w + o.att_b : nullptr, cfg->attention, es, Hh, E);
+      HD_CHECK_LAUNCH();
+    }
+    // 6. c1 = SiLU(m . Wc0^T + bc0)
+    g.X1 = WF(W.m); g.X2 = g.X1; g.W = w + o.coord0_w; g.bias = w + o.coord0_b; g.Y = WF(W.c1);
+    if ((rc = egcl::gemm(st, g))) return rc;
+  }
+  // 7. + 8. coordinate update and message aggregation over `col`
+  if (dense) {
+    egcl::node_reduce_k<<<BN, 256, N * sizeof(float), st>>>(WF(W.m), WF(W.c1), w + o.coord2_w, x, sizes, N, Hh, cfg->tanh,
+                                                          cfg->coords_range, WF(W.agg), x_out);
+    HD_CHECK_LAUNCH();
+  } else {
+    HD_CHECK_CUDA(cudaMemsetAsync(WF(W.agg), 0, (size_t)BN * Hh * 4, st));
+    HD_CHECK_CUDA(cudaMemsetAsync(WF(W.xacc), 0, (size_t)BN * 3 * 4, st));
+    if (E > 0) {
+      egcl::scatter_k<<<(E + 7) / 8, 256, 0, st>>>(WF(W.m), WF(W.c1), w + o.coord2_w, x, es, Hh, cfg->tanh, cfg->coords_range,
+                                               E, WF(W.agg), WF(W.xacc));
+      HD_CHECK_LAUNCH();
+    }
+    egcl::x_finish_k<<<(BN * 3 + 255) / 256, 256, 0, st>>>(x, WF(W.xacc), ns, BN * 3, x_out);
+    HD_CHECK_LAUNCH();
+  }
+  // 11. + 12. edge update: e' = (SiLU([m | radial | e] . U1^T + d1) . U2^T + d2) * edge_mask * edge_mask
+  if (cfg->edge_update && E > 0) {
+    g = egcl::GemmArgs{};
+    g.X1 = WF(W.m); g.K1 = Hh; g.ld1 = Hh; g.c1 = 0;
+    g.X2 = edge_attr; g.K2 = De; g.ld2 = De; g.c2 = Hh + 1;
+    g.s = radial; g.cs = Hh;
+    g.W = w + o.edge0_w; g.ldw = ld_edge; g.bias = w + o.edge0_b; g.M = E; g.Nout = Hh; g.ldy = Hh; g.Y = WF(W.e1); g.act = 1;
+    if ((rc = egcl::gemm(st, g))) return rc;
+    g = egcl::GemmArgs{};
+    g.X1 = WF(W.e1); g.X2 = g.X1; g.K1 = Hh; g.ld1 = Hh; g.ld2 = Hh; g.W = w + o.edge2_w; g.ldw = Hh; g.bias = w + o.edge2_b;
+    g.M = E; g.Nout = Hh; g.ldy = Hh; g.Y = edge_out; g.mask_mode = has_emask ? 2 : 0; g.mask_twice = 1; g.es = es;
+    if ((rc = egcl::gemm(st, g))) return rc;
+  }
+  // 9. hid = SiLU([h | agg] . V1^T + c1)
+  g = egcl::GemmArgs{};
+  g.X1 = h; g.K1 = Hh; g.ld1 = Hh; g.c1 = 0; g.X2 = WF(W.agg); g.K2 = Hh; g.ld2 = Hh; g.c2 = Hh;
+  g.W = w + o.node0_w; g.ldw = 2 * Hh; g.bias = w + o.node0_b; g.M = BN; g.Nout = Hh; g.ldy = Hh; g.Y = WF(W.hid); g.act = 1;
+  if ((rc = egcl::gemm(st, g))) return rc;
+  // 10. h' = (h + hid . V2^T + c2) * node_mask
+  g = egcl::GemmArgs{};
+  g.X1 = WF(W.hid); g.X2 = g.X1; g.K1 = Hh; g.ld1 = Hh; g.ld2 = Hh; g.W = w + o.node2_w; g.ldw = Hh; g.bias = w + o.node2_b;
+  g.M = BN; g.Nout = Hh; g.ldy = Hh; g.Y = h_out; g.resid = h; g.mask_mode = has_nmask ? 1 : 0; g.ns = ns;
+  if ((rc = egcl::gemm(st, g))) return rc;
+  return HD_OK;
+}
+
+}  // extern "C"

@@ -20,7 +20,7 @@ FLAG_NAN = 1
 FLAG_COG = 2
 FLAG_MASK = 4
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class HdConfig(ctypes.Structure):
@@ -32,6 +32,12 @@ class HdConfig(ctypes.Structure):
                 ("normalization_factor", ctypes.c_float), ("aggregation_mean", ctypes.c_int32)]
 
 
+class HdEgclConfig(ctypes.Structure):
+    """``hd_egcl_config`` (stage-2 E_GCL hyper-parameters, reference ROOT models/egnn/gcl.py:18)."""
+    _fields_ = [("hidden_nf", ctypes.c_int32), ("edges_in_d", ctypes.c_int32), ("attention", ctypes.c_int32),
+                ("tanh", ctypes.c_int32), ("coords_range", ctypes.c_float), ("edge_update", ctypes.c_int32)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -40,6 +46,8 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int32
 _F = ctypes.c_float
 _CFG = ctypes.POINTER(HdConfig)
+_ECFG = ctypes.POINTER(HdEgclConfig)
+_L = ctypes.c_int64
 
 # name -> (restype, argtypes); mirrors include/hierdiff_b200.h one to one
 SIGNATURES = {
@@ -67,6 +75,9 @@ SIGNATURES = {
     "hd_sampler_step": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
     "hd_sampler_final": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P,
                               _I, _P]),
+    "hd_egcl_weight_count": (_L, [_ECFG]),
+    "hd_egcl_workspace_bytes": (_L, [_ECFG, _L, _L]),
+    "hd_egcl_forward": (_I, [_ECFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 6
+#define HD_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -209,6 +209,35 @@ HD_API int32_t hd_sampler_final(const hd_config* cfg, const void* packed, const 
 HD_API int32_t hd_edge_kernel_only(const hd_config* cfg, const void* packed, int32_t block, int32_t sub,
                                    const float* x, const float* x0, const int32_t* sizes, int32_t B, int32_t N,
                                    void* workspace, int32_t engine, hd_stream_t stream);
+
+/* ---- stage-2 fine-grained decoder layer: one E_GCL of the reference ROOT models/egnn/gcl.py:9-209 as
+ * models/edge_denoise.py:35-43 builds it (recurrent, agg = 'sum', coord_update, context_nf = 0, geo = False).  Replaces
+ * E_GCL.forward (gcl.py:167-199).  `w` = the layer's parameters, flat fp32 in state_dict order:
+ *   mes_mlp.0.{weight [H, 2H+1+De], bias}, mes_mlp.2.{weight [H,H], bias}, [edge_mlp.0.{weight [H, H+1+De], bias},
+ *   edge_mlp.2.{weight, bias} if edge_update], node_mlp.0.{weight [H,2H], bias}, node_mlp.2.{weight, bias},
+ *   coord_mlp.0.{weight, bias}, coord_mlp.2.weight [1,H], [att_mlp.0.{weight [1,H], bias [1]} if attention].
+ * Edges: row == NULL selects the DENSE list of edge_denoise.py:506-524 (edge e = (b, i, j), row = b*N+i, col = b*N+j,
+ * n_nodes = B*N, n_edges = B*N*N) with node_mask / edge_mask derived from `sizes` (prefix node masks, off-diagonal
+ * edge masks; edge_mask / node_mask arguments ignored); otherwise row/col [n_edges] index the n_nodes rows of h and
+ * edge_mask [n_edges] / node_mask [n_nodes] are optional float multipliers (NULL = the reference's None) and
+ * sizes (NULL) / B / N are ignored; an empty list (n_edges = 0, all edge pointers NULL) is valid.  Messages aggregate over `col` (gcl.py:121).  h, h_out [n_nodes, H]; x, x_out
+ * [n_nodes, 3] (x_out must not alias x); edge_attr [n_edges, De]; edge_out [n_edges, H] when edge_update (may alias
+ * nothing).  The dense reduction is deterministic; the explicit list is reduced with fp32 atomics. */
+typedef struct {
+  int32_t hidden_nf;    /* H: input_nf = output_nf = hidden_nf */
+  int32_t edges_in_d;   /* De */
+  int32_t attention;
+  int32_t tanh;
+  float coords_range;
+  int32_t edge_update;
+} hd_egcl_config;
+HD_API int64_t hd_egcl_weight_count(const hd_egcl_config* cfg);
+HD_API int64_t hd_egcl_workspace_bytes(const hd_egcl_config* cfg, int64_t n_nodes, int64_t n_edges);
+HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const float* h, const float* x,
+                               const float* edge_attr, const int32_t* row, const int32_t* col, const float* edge_mask,
+                               const float* node_mask, const int32_t* sizes, int32_t B, int32_t N, int64_t n_nodes,
+                               int64_t n_edges, float* h_out, float* x_out, float* edge_out, void* workspace,
+                               hd_stream_t stream);
 
 #ifdef __cplusplus
 }

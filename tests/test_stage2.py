@@ -1,0 +1,179 @@
+"""Stage-2 decoder layer ``E_GCL`` (reference ROOT models/egnn/gcl.py).
+
+CPU: the numpy oracle (oracle/egcl_oracle.py) is pinned to fixtures recorded from the unmodified reference
+(tests/golden/make_golden_stage2.py).  GPU: ``hierdiff_b200.E_GCL`` (-> hd_egcl_forward through the C ABI) against the
+same fixtures and against the oracle on larger seeded inputs.  Tolerances are relative to max|ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import egcl_oracle as EO
+from weightgen import fill_state_dict
+
+H = 256
+CASES = ["egcl_full", "egcl_plain", "egcl_focal", "egcl_edge"]
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def layer_shapes(De, attention, edge_update):
+    s = {"mes_mlp.0.weight": (H, 2 * H + 1 + De), "mes_mlp.0.bias": (H,), "mes_mlp.2.weight": (H, H), "mes_mlp.2.bias": (H,)}
+    if edge_update:
+        s.update({"edge_mlp.0.weight": (H, H + 1 + De), "edge_mlp.0.bias": (H,), "edge_mlp.2.weight": (H, H),
+                  "edge_mlp.2.bias": (H,)})
+    s.update({"node_mlp.0.weight": (H, 2 * H), "node_mlp.0.bias": (H,), "node_mlp.2.weight": (H, H), "node_mlp.2.bias": (H,),
+              "coord_mlp.0.weight": (H, H), "coord_mlp.0.bias": (H,), "coord_mlp.2.weight": (1, H)})
+    if attention:
+        s.update({"att_mlp.0.weight": (1, H), "att_mlp.0.bias": (1,)})
+    return s
+
+
+def fixture_weights(name, De, attention, edge_update):
+    shapes = layer_shapes(De, attention, edge_update)
+    filled = fill_state_dict({"stage2." + name + "." + k: s for k, s in shapes.items()}, 2022)
+    return {k: filled["stage2." + name + "." + k] for k in shapes}
+
+
+def masks(sizes, N):
+    B = len(sizes)
+    nm = (np.arange(N)[None, :] < np.asarray(sizes)[:, None]).astype(np.float32)
+    em = nm[:, :, None] * nm[:, None, :] * (1 - np.eye(N, dtype=np.float32))[None]
+    return nm.reshape(B * N, 1), em.reshape(B * N * N, 1)
+
+
+def load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    De, att, eu = int(g["edges_in_d"]), bool(g["attention"]), bool(g["edge_update"])
+    return g, fixture_weights(name, De, att, eu), De, att, eu
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(golden_dir, name):
+    g, w, De, att, eu = load(golden_dir, name)
+    nm, em = masks(g["sizes"], int(g["N"]))
+    if not int(g["dense"]):
+        em = None
+    h, x, e = EO.egcl_forward(w, g["h"], g["x"], g["edge_attr"], nm, em, g["row"], g["col"], att, True, 30.0, eu)
+    assert rel(h, g["h_out"]) < 2e-6
+    assert rel(x, g["x_out"]) < 2e-6
+    if eu:
+        assert rel(e, g["edge_out"]) < 2e-6
+    else:
+        assert e is None
+
+
+def test_mirror_state_dict_matches_reference_layout():
+    """hierdiff_b200.E_GCL carries the reference's parameter names and shapes, in the reference's order."""
+    from hierdiff_b200 import E_GCL
+    for De, att, eu in ((H, True, True), (1, False, False), (H, False, True)):
+        layer = E_GCL(H, H, H, edges_in_d=De, attention=att, tanh=True, coords_range=30, edge_update=eu)
+        got = {k: tuple(v.shape) for k, v in layer.state_dict().items()}
+        assert list(got.items()) == list(layer_shapes(De, att, eu).items())
+        from hierdiff_b200 import native
+        assert native.lib().hd_egcl_weight_count(layer.native_config()) == sum(int(np.prod(s)) for s in got.values())
+    with pytest.raises(NotImplementedError):
+        E_GCL(H, H, H, edges_in_d=1, agg="mean")
+    with pytest.raises(native.NativeError):
+        layer(torch.zeros(4, H), [torch.zeros(1, dtype=torch.long)] * 2, torch.zeros(4, 3), edge_attr=torch.zeros(1, H))
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def make_layer(name, De, att, eu, dev):
+    from hierdiff_b200 import E_GCL
+    layer = E_GCL(H, H, H, edges_in_d=De, attention=att, tanh=True, coords_range=30, edge_update=eu)
+    w = fixture_weights(name, De, att, eu)
+    layer.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    return layer.to(dev), w
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("path", ["list", "dense"])
+def test_cuda_layer_matches_reference_fixture(golden_dir, name, path):
+    g, _, De, att, eu = load(golden_dir, name)
+    dense = bool(int(g["dense"]))
+    if path == "dense" and not dense:
+        pytest.skip("explicit-list fixture")
+    dev = torch.device("cuda", 0)
+    layer, _ = make_layer(name, De, att, eu, dev)
+    N, sizes = int(g["N"]), g["sizes"]
+    B = len(sizes)
+    nm, em = masks(sizes, N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if path == "dense":
+        out = layer.forward_dense(T(g["h"]), T(g["x"]), T(g["edge_attr"]), T(sizes.astype(np.int32)), B, N)
+    else:
+        edges = [T(g["row"].astype(np.int64)), T(g["col"].astype(np.int64))]
+        out = layer(T(g["h"]), edges, T(g["x"]), edge_attr=T(g["edge_attr"]), node_mask=T(nm),
+                    edge_mask=T(em) if dense else None)
+    assert rel(out[0].cpu().numpy(), g["h_out"]) < 5e-6
+    assert rel(out[1].cpu().numpy(), g["x_out"]) < 5e-6
+    if eu:
+        assert rel(out[2].cpu().numpy(), g["edge_out"]) < 5e-6
+    else:
+        assert len(out) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("De,att,eu", [(H, True, True), (1, False, False)])
+def test_cuda_layer_matches_oracle_stack(De, att, eu):
+    """Three chained layers on a ragged dense batch (the gcl_full_* stack of sample_AR, edge_denoise.py:293-294):
+    dense path == explicit-list path == oracle; the dense path is bit-reproducible."""
+    dev = torch.device("cuda", 0)
+    sizes, N = [12, 5, 1, 9, 12, 7], 12
+    B = len(sizes)
+    rng = np.random.default_rng(5)
+    nm, em = masks(sizes, N)
+    h = (rng.standard_normal((B * N, H)).astype(np.float32) * nm)
+    x = (rng.standard_normal((B * N, 3)).astype(np.float32) * nm)
+    e = (rng.standard_normal((B * N * N, De)).astype(np.float32) * em)
+    row, col = EO.dense_edges(B, N)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    edges = [T(row.astype(np.int64)), T(col.astype(np.int64))]
+    sz = T(np.array(sizes, np.int32))
+    hd, xd, ed = T(h), T(x), T(e)
+    hl, xl, el = T(h), T(x), T(e)
+    ho, xo, eo = h, x, e
+    for li in range(3):
+        layer, w = make_layer("stack%d" % li, De, att, eu, dev)
+        od = layer.forward_dense(hd, xd, ed, sz, B, N)
+        od2 = layer.forward_dense(hd, xd, ed, sz, B, N)
+        assert all(torch.equal(a, b) for a, b in zip(od, od2))
+        ol = layer(hl, edges, xl, edge_attr=el, node_mask=T(nm), edge_mask=T(em))
+        oo = EO.egcl_forward(w, ho, xo, eo, nm, em, row, col, att, True, 30.0, eu)
+        hd, xd = od[0], od[1]
+        hl, xl = ol[0], ol[1]
+        ho, xo = oo[0], oo[1]
+        if eu:
+            ed, el, eo = od[2], ol[2], oo[2]
+        for got in ((hd, xd, ed), (hl, xl, el)):
+            assert rel(got[0].cpu().numpy(), ho) < 1e-5
+            assert rel(got[1].cpu().numpy(), xo) < 1e-5
+            assert rel(got[2].cpu().numpy(), eo) < 1e-5
+        # padded rows stay exactly zero
+        assert float((hd * (1 - T(nm))).abs().max()) == 0.0 and float((xd * (1 - T(nm))).abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_cuda_layer_empty_and_unmasked_lists():
+    """An empty edge list (a BFS depth without edges) and a list without any mask (gcl.py: node_mask=None)."""
+    dev = torch.device("cuda", 0)
+    layer, w = make_layer("edgecase", 1, False, False, dev)
+    rng = np.random.default_rng(6)
+    n = 10
+    h = rng.standard_normal((n, H)).astype(np.float32)
+    x = rng.standard_normal((n, 3)).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for E in (0, 23):
+        row = rng.integers(0, n, E)
+        col = rng.integers(0, n, E)
+        e = rng.standard_normal((E, 1)).astype(np.float32)
+        out = layer(T(h), [T(row), T(col)], T(x), edge_attr=T(e))
+        want = EO.egcl_forward(w, h, x, e, None, None, row, col, False, True, 30.0, False)
+        assert rel(out[0].cpu().numpy(), want[0]) < 1e-5
+        assert rel(out[1].cpu().numpy(), want[1]) < 1e-5
