@@ -313,6 +313,18 @@ HD_API int64_t hd_egcl_workspace_bytes(const hd_egcl_config* cfg, int64_t n_node
   return egcl::work(*cfg, n_nodes, n_edges).total;
 }
 
+HD_API int32_t hd_linear_forward(const float* x, int64_t rows, int32_t in_nf, const float* weight, const float* bias,
+                                 int32_t out_nf, int32_t act, float* y, hd_stream_t stream) {
+  if (!x || !weight || !y || rows < 0 || in_nf < 1 || out_nf < 1 || act < 0 || act > 1 || rows > 0x7fffffff / 4) {
+    set_error("hd_linear_forward: bad argument");
+    return HD_E_INVALID;
+  }
+  egcl::GemmArgs g{};
+  g.X1 = x; g.X2 = x; g.K1 = in_nf; g.ld1 = in_nf; g.ld2 = in_nf; g.W = weight; g.ldw = in_nf; g.bias = bias;
+  g.M = (int)rows; g.Nout = out_nf; g.ldy = out_nf; g.Y = y; g.act = act;
+  return egcl::gemm(static_cast<cudaStream_t>(stream), g);
+}
+
 HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const float* h, const float* x,
                                const float* edge_attr, const int32_t* row, const int32_t* col, const float* edge_mask,
                                const float* node_mask, const int32_t* sizes, int32_t B, int32_t N, int64_t n_nodes,

@@ -75,6 +75,7 @@ SIGNATURES = {
     "hd_sampler_step": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
     "hd_sampler_final": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P,
                               _I, _P]),
+    "hd_linear_forward": (_I, [_P, _L, _I, _P, _P, _I, _I, _P, _P]),
     "hd_egcl_weight_count": (_L, [_ECFG]),
     "hd_egcl_workspace_bytes": (_L, [_ECFG, _L, _L]),
     "hd_egcl_forward": (_I, [_ECFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _P]),

@@ -137,7 +137,8 @@ def dense_sizes(node_mask, edge_mask, edge_index, B, N):
     try:
         sizes = sizes_from_node_mask(node_mask.reshape(B, N, 1), B, N)
         check_edge_mask(edge_mask, sizes, B, N)
-        check_edge_index(edge_index, B, N)
+        if edge_index is not None:
+            check_edge_index(edge_index, B, N)
     except (NotImplementedError, ValueError, AssertionError):
         return None
     return sizes

@@ -231,6 +231,10 @@ typedef struct {
   float coords_range;
   int32_t edge_update;
 } hd_egcl_config;
+/* y [rows, out_nf] = act(x [rows, in_nf] . weight^T + bias): one nn.Linear (weight [out_nf, in_nf] row-major, bias may be
+ * NULL), act 0 = none, 1 = SiLU.  The embeddings and prediction heads of Edge_denoise (edge_denoise.py:27-31, :54-56). */
+HD_API int32_t hd_linear_forward(const float* x, int64_t rows, int32_t in_nf, const float* weight, const float* bias,
+                                 int32_t out_nf, int32_t act, float* y, hd_stream_t stream);
 HD_API int64_t hd_egcl_weight_count(const hd_egcl_config* cfg);
 HD_API int64_t hd_egcl_workspace_bytes(const hd_egcl_config* cfg, int64_t n_nodes, int64_t n_edges);
 HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const float* h, const float* x,

@@ -13,7 +13,8 @@ import numpy as np
 
 
 def silu(v):
-    return v / (1.0 + np.exp(-v))
+    with np.errstate(over="ignore"):      # exp(-v) -> inf for very negative v: v / inf = -0, as ATen's SiLU
+        return v / (1.0 + np.exp(-v))
 
 
 def linear(x, w, b=None):

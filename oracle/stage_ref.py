@@ -48,6 +48,11 @@ FILES = [
     "models/egnn/gcl.py",
     "models/egnn/egnn_new.py",
     "models/egnn/utils.py",
+    "models/edge_denoise.py",
+    "models/flows/__init__.py",
+    "models/flows/utils.py",
+    "data_utils/data_diffuse.py",     # only its breadth-first helpers are ever executed (make_golden_stage2.import_edge_denoise)
+    "conf/model/edge_denoise.yaml",
 ]
 
 
