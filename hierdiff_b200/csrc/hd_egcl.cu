@@ -21,6 +21,12 @@
 #include "hd_common.cuh"
 
 namespace hd {
+int linear_tc_rows(cudaStream_t st, int rows, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2,
+                   const void* w_hi, const void* w_lo, int n_out, const float* bias, float* Y, int ldy, int mode,
+                   const float* resid, const float* s, const float* ws, const float* ab, const int32_t* sizes, int N,
+                   bool strict);
+int make_image128(const float* src, int ld, int row0, int col0, int n_out, int K, int k_at, int k_total, void* hi, void* lo,
+                  cudaStream_t st);
 namespace egcl {
 
 struct Offsets {   // float offsets into the flat state_dict-order parameter buffer (-1: absent)
@@ -48,6 +54,37 @@ static Offsets offsets(const hd_egcl_config& c) {
   if (c.attention) { o.att_w = take(Hh); o.att_b = take(1); } else { o.att_w = o.att_b = -1; }
   o.total = s;
   return o;
+}
+
+// Packed image for the tensor-core path (dense list, hidden_nf = edges_in_d = 256): bf16 hi / lo operand images of every
+// Linear in 128-row output tiles (hd_node.cu) + the fp32 vectors its epilogues read.  Byte offsets, 256-aligned.
+struct Pack {
+  int64_t ab_hi, ab_lo, ab_bias;   // [2H out][H k]: mes_mlp.0 columns [0, H) | [H, 2H); bias [b | 0]
+  int64_t we_hi, we_lo, w_r;       // [H][De]: mes_mlp.0 columns [2H+1, ...); w_r = column 2H
+  int64_t w2_hi, w2_lo;            // mes_mlp.2
+  int64_t wc_hi, wc_lo;            // coord_mlp.0
+  int64_t u1_hi, u1_lo, u_r;       // [H][H + De]: edge_mlp.0 columns [0, H) | [H+1, ...); u_r = column H
+  int64_t u2_hi, u2_lo;            // edge_mlp.2
+  int64_t v1_hi, v1_lo;            // node_mlp.0 [H][2H]
+  int64_t v2_hi, v2_lo;            // node_mlp.2
+  int64_t total;
+};
+static bool tc_shape(const hd_egcl_config& c) { return c.hidden_nf == 256 && c.edges_in_d == 256; }
+static Pack pack_layout(const hd_egcl_config& c) {
+  Pack k{};
+  const int64_t Hh = c.hidden_nf, De = c.edges_in_d;
+  int64_t p = 0;
+  auto put = [&](int64_t bytes) { int64_t r = p; p = (p + bytes + 255) & ~int64_t(255); return r; };
+  k.ab_hi = put(2 * Hh * Hh * 2); k.ab_lo = put(2 * Hh * Hh * 2); k.ab_bias = put(2 * Hh * 4);
+  k.we_hi = put(Hh * De * 2); k.we_lo = put(Hh * De * 2); k.w_r = put(Hh * 4);
+  k.w2_hi = put(Hh * Hh * 2); k.w2_lo = put(Hh * Hh * 2);
+  k.wc_hi = put(Hh * Hh * 2); k.wc_lo = put(Hh * Hh * 2);
+  k.u1_hi = put(Hh * (Hh + De) * 2); k.u1_lo = put(Hh * (Hh + De) * 2); k.u_r = put(Hh * 4);
+  k.u2_hi = put(Hh * Hh * 2); k.u2_lo = put(Hh * Hh * 2);
+  k.v1_hi = put(Hh * 2 * Hh * 2); k.v1_lo = put(Hh * 2 * Hh * 2);
+  k.v2_hi = put(Hh * Hh * 2); k.v2_lo = put(Hh * Hh * 2);
+  k.total = p;
+  return k;
 }
 
 struct Work {   // byte offsets, 256-aligned
@@ -288,6 +325,20 @@ __global__ void x_finish_k(const float* __restrict__ x, const float* __restrict_
   if (idx < count) x_out[idx] = (x[idx] + xacc[idx]) * node_get(ns, idx / 3);
 }
 
+// dst[o] = src[o * ld + col] (o < n); col < 0: dst[o] = o < n_src ? src[o] : 0   (bias image [b | 0])
+__global__ void vec_k(const float* __restrict__ src, int ld, int col, int n, int n_src, float* __restrict__ dst) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  dst[o] = col >= 0 ? src[(int64_t)o * ld + col] : (o < n_src ? src[o] : 0.f);
+}
+__global__ void radial_dense_k(const float* __restrict__ x, int N, int64_t E, float* __restrict__ radial) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t row = e / N, col = (e / ((int64_t)N * N)) * N + e % N;
+  const float d0 = x[row * 3] - x[col * 3], d1 = x[row * 3 + 1] - x[col * 3 + 1], d2 = x[row * 3 + 2] - x[col * 3 + 2];
+  radial[e] = d0 * d0 + d1 * d1 + d2 * d2;
+}
+
 static int gemm(cudaStream_t st, const GemmArgs& a) {
   if (a.M < 1) return HD_OK;
   dim3 grid((a.M + 63) / 64, (a.Nout + 63) / 64);
@@ -325,11 +376,107 @@ HD_API int32_t hd_linear_forward(const float* x, int64_t rows, int32_t in_nf, co
   return egcl::gemm(static_cast<cudaStream_t>(stream), g);
 }
 
-HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const float* h, const float* x,
-                               const float* edge_attr, const int32_t* row, const int32_t* col, const float* edge_mask,
-                               const float* node_mask, const int32_t* sizes, int32_t B, int32_t N, int64_t n_nodes,
-                               int64_t n_edges, float* h_out, float* x_out, float* edge_out, void* workspace,
-                               hd_stream_t stream) {
+HD_API int64_t hd_egcl_packed_bytes(const hd_egcl_config* cfg) {
+  if (!cfg) return HD_E_INVALID;
+  return egcl::tc_shape(*cfg) ? egcl::pack_layout(*cfg).total : 0;
+}
+
+HD_API int32_t hd_egcl_pack_weights(const hd_egcl_config* cfg, const float* w, void* packed, hd_stream_t stream) {
+  if (!cfg || !w || !packed || !egcl::tc_shape(*cfg)) {
+    set_error("hd_egcl_pack_weights: the tensor-core path needs hidden_nf = edges_in_d = 256");
+    return HD_E_INVALID;
+  }
+  const egcl::Offsets o = egcl::offsets(*cfg);
+  const egcl::Pack K = egcl::pack_layout(*cfg);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* P = static_cast<char*>(packed);
+  auto PF = [&](int64_t off) { return reinterpret_cast<float*>(P + off); };
+  const int Hh = cfg->hidden_nf, De = cfg->edges_in_d, ld_mes = 2 * Hh + 1 + De, ld_edge = Hh + 1 + De;
+  int rc;
+  // A | B: outputs [0, H) from mes_mlp.0 columns [0, H), outputs [H, 2H) from columns [H, 2H)
+  for (int part = 0; part < 2; ++part)
+    for (int t = 0; t < Hh / 128; ++t) {
+      const int64_t off = (int64_t)(part * (Hh / 128) + t) * 128 * Hh * 2;
+      if ((rc = make_image128(w + o.mes0_w, ld_mes, t * 128, part * Hh, 128, Hh, 0, Hh, P + K.ab_hi + off, P + K.ab_lo + off, st)))
+        return rc;
+    }
+  egcl::vec_k<<<(2 * Hh + 255) / 256, 256, 0, st>>>(w + o.mes0_b, 0, -1, 2 * Hh, Hh, PF(K.ab_bias));
+  if ((rc = make_image128(w + o.mes0_w, ld_mes, 0, 2 * Hh + 1, Hh, De, 0, De, P + K.we_hi, P + K.we_lo, st))) return rc;
+  egcl::vec_k<<<(Hh + 255) / 256, 256, 0, st>>>(w + o.mes0_w, ld_mes, 2 * Hh, Hh, Hh, PF(K.w_r));
+  if ((rc = make_image128(w + o.mes2_w, Hh, 0, 0, Hh, Hh, 0, Hh, P + K.w2_hi, P + K.w2_lo, st))) return rc;
+  if ((rc = make_image128(w + o.coord0_w, Hh, 0, 0, Hh, Hh, 0, Hh, P + K.wc_hi, P + K.wc_lo, st))) return rc;
+  if (cfg->edge_update) {
+    if ((rc = make_image128(w + o.edge0_w, ld_edge, 0, 0, Hh, Hh, 0, Hh + De, P + K.u1_hi, P + K.u1_lo, st))) return rc;
+    if ((rc = make_image128(w + o.edge0_w, ld_edge, 0, Hh + 1, Hh, De, Hh, Hh + De, P + K.u1_hi, P + K.u1_lo, st))) return rc;
+    egcl::vec_k<<<(Hh + 255) / 256, 256, 0, st>>>(w + o.edge0_w, ld_edge, Hh, Hh, Hh, PF(K.u_r));
+    if ((rc = make_image128(w + o.edge2_w, Hh, 0, 0, Hh, Hh, 0, Hh, P + K.u2_hi, P + K.u2_lo, st))) return rc;
+  }
+  if ((rc = make_image128(w + o.node0_w, 2 * Hh, 0, 0, Hh, 2 * Hh, 0, 2 * Hh, P + K.v1_hi, P + K.v1_lo, st))) return rc;
+  if ((rc = make_image128(w + o.node2_w, Hh, 0, 0, Hh, Hh, 0, Hh, P + K.v2_hi, P + K.v2_lo, st))) return rc;
+  HD_CHECK_LAUNCH();
+  return HD_OK;
+}
+
+// the dense list on the tensor cores: every Linear through lin::linear_tc_k (tcgen05, bf16x3 split operands in strict
+// mode), the per-edge glue folded into its epilogues (hd_node.cu modes 4-6)
+static int egcl_dense_tc(const hd_egcl_config* cfg, const float* w, const char* P, const float* h, const float* x,
+                         const float* edge_attr, const int32_t* sizes, int B, int N, float* h_out, float* x_out,
+                         float* edge_out, char* ws, cudaStream_t st, bool strict) {
+  const egcl::Offsets o = egcl::offsets(*cfg);
+  const egcl::Pack K = egcl::pack_layout(*cfg);
+  const int Hh = cfg->hidden_nf, De = cfg->edges_in_d, BN = B * N, E = BN * N;
+  const egcl::Work W = egcl::work(*cfg, BN, E);
+  auto WF = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto PF = [&](int64_t off) { return reinterpret_cast<const float*>(P + off); };
+  float* radial = WF(W.radial);
+  int rc;
+  egcl::radial_dense_k<<<(E + 255) / 256, 256, 0, st>>>(x, N, E, radial);
+  HD_CHECK_LAUNCH();
+  // A|B = h . [W1a | W1b]^T + [b1 | 0]
+  if ((rc = linear_tc_rows(st, BN, h, Hh, Hh, nullptr, 0, 0, P + K.ab_hi, P + K.ab_lo, 2 * Hh, PF(K.ab_bias), WF(W.ab), 2 * Hh, 0,
+                           nullptr, nullptr, nullptr, nullptr, sizes, N, strict)))
+    return rc;
+  // m1 = SiLU(e . We^T + radial * w_r + A_row + B_col)
+  if ((rc = linear_tc_rows(st, E, edge_attr, De, De, nullptr, 0, 0, P + K.we_hi, P + K.we_lo, Hh, nullptr, WF(W.m1), Hh, 6,
+                           nullptr, radial, PF(K.w_r), WF(W.ab), sizes, N, strict)))
+    return rc;
+  // m2 = SiLU(m1 . W2^T + b2); attention gate and edge mask
+  if ((rc = linear_tc_rows(st, E, WF(W.m1), Hh, Hh, nullptr, 0, 0, P + K.w2_hi, P + K.w2_lo, Hh, w + o.mes2_b, WF(W.m), Hh, 1,
+                           nullptr, nullptr, nullptr, nullptr, sizes, N, strict)))
+    return rc;
+  const egcl::EdgeSrc es{nullptr, nullptr, nullptr, sizes, N};
+  egcl::att_k<<<(E + 7) / 8, 256, 0, st>>>(WF(W.m), cfg->attention ? w + o.att_w : nullptr,
+                                       cfg->attention ? w + o.att_b : nullptr, cfg->attention, es, Hh, E);
+  HD_CHECK_LAUNCH();
+  // c1 = SiLU(m . Wc0^T + bc0); coordinate update and aggregation over col
+  if ((rc = linear_tc_rows(st, E, WF(W.m), Hh, Hh, nullptr, 0, 0, P + K.wc_hi, P + K.wc_lo, Hh, w + o.coord0_b, WF(W.c1), Hh, 1,
+                           nullptr, nullptr, nullptr, nullptr, sizes, N, strict)))
+    return rc;
+  egcl::node_reduce_k<<<BN, 256, N * sizeof(float), st>>>(WF(W.m), WF(W.c1), w + o.coord2_w, x, sizes, N, Hh, cfg->tanh,
+                                                        cfg->coords_range, WF(W.agg), x_out);
+  HD_CHECK_LAUNCH();
+  if (cfg->edge_update) {
+    // e1 = SiLU([m | e] . U1^T + radial * u_r + d1); e' = (e1 . U2^T + d2) * edge_mask
+    if ((rc = linear_tc_rows(st, E, WF(W.m), Hh, Hh, edge_attr, De, De, P + K.u1_hi, P + K.u1_lo, Hh, w + o.edge0_b, WF(W.e1),
+                             Hh, 4, nullptr, radial, PF(K.u_r), nullptr, sizes, N, strict)))
+      return rc;
+    if ((rc = linear_tc_rows(st, E, WF(W.e1), Hh, Hh, nullptr, 0, 0, P + K.u2_hi, P + K.u2_lo, Hh, w + o.edge2_b, edge_out, Hh, 5,
+                             nullptr, nullptr, nullptr, nullptr, sizes, N, strict)))
+      return rc;
+  }
+  // hid = SiLU([h | agg] . V1^T + c1); h' = (h + hid . V2^T + c2) * node_mask
+  if ((rc = linear_tc_rows(st, BN, h, Hh, Hh, WF(W.agg), Hh, Hh, P + K.v1_hi, P + K.v1_lo, Hh, w + o.node0_b, WF(W.hid), Hh, 1,
+                           nullptr, nullptr, nullptr, nullptr, sizes, N, strict)))
+    return rc;
+  return linear_tc_rows(st, BN, WF(W.hid), Hh, Hh, nullptr, 0, 0, P + K.v2_hi, P + K.v2_lo, Hh, w + o.node2_b, h_out, Hh, 2, h,
+                        nullptr, nullptr, nullptr, sizes, N, strict);
+}
+
+HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const void* packed, const float* h,
+                               const float* x, const float* edge_attr, const int32_t* row, const int32_t* col,
+                               const float* edge_mask, const float* node_mask, const int32_t* sizes, int32_t B, int32_t N,
+                               int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out, float* edge_out,
+                               void* workspace, int32_t engine, hd_stream_t stream) {
   if (!cfg || !w || !h || !x || !h_out || !x_out || !workspace) {
     set_error("null argument");
     return HD_E_INVALID;
@@ -362,6 +509,18 @@ HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const 
   const egcl::Work W = egcl::work(*cfg, n_nodes, n_edges);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
+  if (engine != HD_ENGINE_FP32) {
+    if (engine != HD_ENGINE_TC_STRICT && engine != HD_ENGINE_TC_FAST) {
+      set_error("unknown engine %d", engine);
+      return HD_E_INVALID;
+    }
+    if (!dense || !packed || !egcl::tc_shape(*cfg)) {
+      set_error("the tensor-core engines run the dense list with hidden_nf = edges_in_d = 256 and a packed weight image");
+      return HD_E_UNSUPPORTED;
+    }
+    return egcl_dense_tc(cfg, w, static_cast<const char*>(packed), h, x, edge_attr, sizes, B, N, h_out, x_out, edge_out, ws,
+                         st, engine == HD_ENGINE_TC_STRICT);
+  }
   auto WF = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
   const int Hh = cfg->hidden_nf, De = cfg->edges_in_d;
   const int BN = (int)n_nodes, E = (int)n_edges;

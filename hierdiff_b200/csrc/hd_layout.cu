@@ -256,6 +256,24 @@ __global__ void image_k(const float* __restrict__ src, int ld, int row0, int col
   lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// image of W[row0 .. row0+n_out) x K columns [col0, col0+K) in 128-row output tiles, written at K offset `k_at` of an
+// image whose full K is `k_total` (hd_node.cu weight layout img[tile][kg < k_total/8][128][8]); the stage-2 layer's packer
+int make_image128(const float* src, int ld, int row0, int col0, int n_out, int K, int k_at, int k_total, void* hi, void* lo,
+                  cudaStream_t st) {
+  for (int t = 0; t < n_out / 128; ++t) {
+    const int64_t o = ((int64_t)t * (k_total / 8) + k_at / 8) * 128 * 8;
+    image_k<<<(128 * K + 255) / 256, 256, 0, st>>>(src, ld, row0 + t * 128, col0, 128, K,
+                                                  reinterpret_cast<__nv_bfloat16*>(hi) + o,
+                                                  reinterpret_cast<__nv_bfloat16*>(lo) + o);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("make_image128: %s", cudaGetErrorString(e));
+    return HD_E_CUDA;
+  }
+  return HD_OK;
+}
+
 int pack_weights(const hd_config& c, const Layout& L, const float* w, char* P, cudaStream_t st) {
   const int T = 256;
   const float NEG_LOG2E = -1.4426950408889634f;

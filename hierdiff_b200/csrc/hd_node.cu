@@ -71,7 +71,12 @@ struct Params {
   float* Y;
   int grid_rows;          // rows the launch covers (<= rows: the caller's bound on the real rows when ragged)
   int ldy, rows, mode;    // mode 0: store, 1: SiLU, 2: (resid + v) * node_mask, 3: store K-chunk-major
-                          // Y[col/16][row][col%16] (the edge kernel's A|B operand layout)
+                          // Y[col/16][row][col%16] (the edge kernel's A|B operand layout); the stage-2 layer
+                          // (hd_egcl.cu), rows = dense edges e = (b, i, j): 4: SiLU(v + s[row] * ws[col]),
+                          // 5: v * edge_mask(row), 6: SiLU(v + s[row] * ws[col] + ab[b*N+i][col] + ab[b*N+j][H + col])
+  const float* s;         // modes 4, 6: per-row scalar (|x_i - x_j|^2)
+  const float* ws;        // modes 4, 6: its weight column [n_out]
+  const float* ab;        // mode 6: [nodes][2 * n_out] per-node halves of the first message Linear
   const float* resid;
   const int32_t* sizes;
   int N;
@@ -271,6 +276,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
         }
       }
       const int col = ct * NT + oc4;
+      if (p.mode >= 4) {
+        if (p.mode == 5) {
+          const int j = row % p.N, i = (row / p.N) % p.N, n = p.sizes[row / (p.N * p.N)];
+          const float mk = (i < n && j < n && i != j) ? 1.f : 0.f;
+          o.x *= mk; o.y *= mk; o.z *= mk; o.w *= mk;
+        } else {
+          const float sv = p.s[row];
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ws + col));
+          o.x = fmaf(sv, w4.x, o.x); o.y = fmaf(sv, w4.y, o.y); o.z = fmaf(sv, w4.z, o.z); o.w = fmaf(sv, w4.w, o.w);
+          if (p.mode == 6) {
+            const int64_t ri = row / p.N, rj = (int64_t)(row / (p.N * p.N)) * p.N + row % p.N;
+            const int nt = p.ldy;   // message width H
+            const float4 a4 = *reinterpret_cast<const float4*>(p.ab + ri * 2 * nt + col);
+            const float4 b4 = *reinterpret_cast<const float4*>(p.ab + rj * 2 * nt + nt + col);
+            o.x += a4.x + b4.x; o.y += a4.y + b4.y; o.z += a4.z + b4.z; o.w += a4.w + b4.w;
+          }
+          o.x = silu_node<STRICT>(o.x); o.y = silu_node<STRICT>(o.y);
+          o.z = silu_node<STRICT>(o.z); o.w = silu_node<STRICT>(o.w);
+        }
+      }
       if (p.mode == 3) *reinterpret_cast<float4*>(p.Y + ((int64_t)(col >> 4) * p.rows + row) * 16 + (col & 15)) = o;
       else *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + col) = o;
     }
@@ -398,6 +423,24 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
   const lin::Params p = make_params(c, X1, ld1, K1, X2, ld2, K2, w_hi, w_lo, bias, Y, ldy, mode, resid);
   if (tile_n == 128) return strict ? lin::launch<true, 128>(p, n_out, c.stream) : lin::launch<false, 128>(p, n_out, c.stream);
   return strict ? lin::launch<true, 64>(p, n_out, c.stream) : lin::launch<false, 64>(p, n_out, c.stream);
+}
+
+// The same kernel for the stage-2 layer (hd_egcl.cu): `rows` of any count (edges or nodes), 128-column output tiles,
+// the epilogue modes 0-2 and 4-6 (Params).
+int linear_tc_rows(cudaStream_t st, int rows, const float* X1, int ld1, int K1, const float* X2, int ld2, int K2,
+                   const void* w_hi, const void* w_lo, int n_out, const float* bias, float* Y, int ldy, int mode,
+                   const float* resid, const float* s, const float* ws, const float* ab, const int32_t* sizes, int N,
+                   bool strict) {
+  if (K1 % lin::KC || K2 % lin::KC || n_out % 128 || (ld1 & 3) || (ld2 & 3) || (ldy & 3) || rows < 1) {
+    set_error("linear_tc_rows: unsupported shape rows=%d K1=%d K2=%d n_out=%d", rows, K1, K2, n_out);
+    return HD_E_INVALID;
+  }
+  lin::Params p{};
+  p.X1 = X1; p.X2 = X2 ? X2 : X1; p.ld1 = ld1; p.K1 = K1; p.ld2 = ld2; p.K2 = K2;
+  p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.Y = Y; p.ldy = ldy; p.rows = rows; p.grid_rows = rows; p.mode = mode;
+  p.resid = resid ? resid : Y; p.sizes = sizes; p.N = N; p.B = 0; p.ragged = 0;
+  p.s = s; p.ws = ws; p.ab = ab;
+  return strict ? lin::launch<true, 128>(p, n_out, st) : lin::launch<false, 128>(p, n_out, st);
 }
 
 // node_mlp.2 (+ residual, mask) -> h_out and, in the same launch, the next sub-layer's A|B pre-projection computed

@@ -52,7 +52,8 @@ class E_GCL(nn.Module):
         self.coord_mlp = nn.Sequential(*coord)
         if attention:
             self.att_mlp = nn.Sequential(nn.Linear(hidden_nf, 1), nn.Sigmoid())
-        self._flat = None      # (version key, flat fp32 parameter buffer on the device)
+        self.engine = "strict"  # dense list with hidden_nf = edges_in_d = 256: "strict" | "fast" (tcgen05) | "fp32"
+        self._flat = None      # (version key, flat fp32 parameter buffer on the device, packed tensor-core image or None)
         self._edges = None     # (row64, col64, row32, col32): int32 copies of the last edge_index (held by identity)
         self._ws = None
 
@@ -70,9 +71,16 @@ class E_GCL(nn.Module):
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
         if self._flat is None or self._flat[0] != key:
             flat = torch.cat([p.detach().reshape(-1).to(device=device, dtype=torch.float32) for p in params])
-            assert flat.numel() == native.lib().hd_egcl_weight_count(self.native_config())
-            self._flat = (key, flat)
-        return self._flat[1]
+            cfg = self.native_config()
+            assert flat.numel() == native.lib().hd_egcl_weight_count(cfg)
+            packed, nbytes = None, native.lib().hd_egcl_packed_bytes(cfg)
+            if nbytes > 0:
+                packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                with torch.cuda.device(device):
+                    native.check(native.lib().hd_egcl_pack_weights(cfg, native.ptr(flat), native.ptr(packed),
+                                                                   native.stream_ptr()), "hd_egcl_pack_weights")
+            self._flat = (key, flat, packed)
+        return self._flat[1], self._flat[2]
 
     def _edge_i32(self, edge_index):
         row, col = edge_index
@@ -119,15 +127,16 @@ class E_GCL(nn.Module):
         if (em is not None and em.numel() != n_edges) or (nm is not None and nm.numel() != n_nodes):
             raise ValueError("mask shapes do not match the edge list / node rows")
         cfg = self.native_config()
-        w = self.flat_weights(dev)
+        w, packed = self.flat_weights(dev)
+        engine = native.ENGINES[self.engine] if (row is None and packed is not None) else native.ENGINE_FP32
         ws = self._workspace(cfg, n_nodes, n_edges, dev)
         h_out, x_out = torch.empty_like(h), torch.empty_like(coord)
         e_out = torch.empty(n_edges, self.hidden_nf, device=dev) if self.edge_update else None
         P = native.ptr
         with torch.cuda.device(dev):
-            native.check(native.lib().hd_egcl_forward(cfg, P(w), P(h), P(coord), P(edge_attr), P(row), P(col), P(em), P(nm),
-                                                      P(sizes), B, N, n_nodes, n_edges, P(h_out), P(x_out), P(e_out),
-                                                      P(ws), native.stream_ptr()), "hd_egcl_forward")
+            native.check(native.lib().hd_egcl_forward(cfg, P(w), P(packed), P(h), P(coord), P(edge_attr), P(row), P(col),
+                                                      P(em), P(nm), P(sizes), B, N, n_nodes, n_edges, P(h_out), P(x_out),
+                                                      P(e_out), P(ws), engine, native.stream_ptr()), "hd_egcl_forward")
         return (h_out, x_out, e_out) if self.edge_update else (h_out, x_out)
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 7
+#define HD_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -237,11 +237,17 @@ HD_API int32_t hd_linear_forward(const float* x, int64_t rows, int32_t in_nf, co
                                  int32_t out_nf, int32_t act, float* y, hd_stream_t stream);
 HD_API int64_t hd_egcl_weight_count(const hd_egcl_config* cfg);
 HD_API int64_t hd_egcl_workspace_bytes(const hd_egcl_config* cfg, int64_t n_nodes, int64_t n_edges);
-HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const float* h, const float* x,
-                               const float* edge_attr, const int32_t* row, const int32_t* col, const float* edge_mask,
-                               const float* node_mask, const int32_t* sizes, int32_t B, int32_t N, int64_t n_nodes,
-                               int64_t n_edges, float* h_out, float* x_out, float* edge_out, void* workspace,
-                               hd_stream_t stream);
+/* Tensor-core engines (HD_ENGINE_TC_STRICT / _FAST) of the layer: the DENSE list with hidden_nf = edges_in_d = 256 (the
+ * gcl_full_* stack, edge_denoise.py:35) runs every Linear on tcgen05 from a packed bf16 hi/lo weight image built once
+ * by hd_egcl_pack_weights (hd_egcl_packed_bytes = 0: this configuration has no tensor-core path).  `packed` may be NULL
+ * with HD_ENGINE_FP32; explicit edge lists always run the fp32 path (they are a few hundred edges). */
+HD_API int64_t hd_egcl_packed_bytes(const hd_egcl_config* cfg);
+HD_API int32_t hd_egcl_pack_weights(const hd_egcl_config* cfg, const float* w, void* packed, hd_stream_t stream);
+HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const void* packed, const float* h,
+                               const float* x, const float* edge_attr, const int32_t* row, const int32_t* col,
+                               const float* edge_mask, const float* node_mask, const int32_t* sizes, int32_t B, int32_t N,
+                               int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out, float* edge_out,
+                               void* workspace, int32_t engine, hd_stream_t stream);
 
 #ifdef __cplusplus
 }

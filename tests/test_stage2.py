@@ -93,14 +93,23 @@ def make_layer(name, De, att, eu, dev):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("path", ["list", "dense"])
+@pytest.mark.parametrize("path", ["list", "dense-fp32", "dense-strict", "dense-fast"])
 def test_cuda_layer_matches_reference_fixture(golden_dir, name, path):
+    """fp32 CUDA-core path, and (hidden edge features) the tcgen05 path with bf16x3 split operands (strict) / single bf16
+    operands (fast), against the fixtures recorded from the unmodified reference."""
     g, _, De, att, eu = load(golden_dir, name)
     dense = bool(int(g["dense"]))
-    if path == "dense" and not dense:
+    if path != "list" and not dense:
         pytest.skip("explicit-list fixture")
+    if path in ("dense-strict", "dense-fast") and De != H:
+        pytest.skip("no tensor-core path for one-column edge features")
     dev = torch.device("cuda", 0)
     layer, _ = make_layer(name, De, att, eu, dev)
+    tol = 5e-6
+    if path != "list":
+        layer.engine = path.split("-")[1]
+        tol = {"fp32": 5e-6, "strict": 1e-5, "fast": 3e-2}[layer.engine]
+    path = path.split("-")[0]
     N, sizes = int(g["N"]), g["sizes"]
     B = len(sizes)
     nm, em = masks(sizes, N)
@@ -111,17 +120,18 @@ def test_cuda_layer_matches_reference_fixture(golden_dir, name, path):
         edges = [T(g["row"].astype(np.int64)), T(g["col"].astype(np.int64))]
         out = layer(T(g["h"]), edges, T(g["x"]), edge_attr=T(g["edge_attr"]), node_mask=T(nm),
                     edge_mask=T(em) if dense else None)
-    assert rel(out[0].cpu().numpy(), g["h_out"]) < 5e-6
-    assert rel(out[1].cpu().numpy(), g["x_out"]) < 5e-6
+    errs = [rel(out[0].cpu().numpy(), g["h_out"]), rel(out[1].cpu().numpy(), g["x_out"])]
     if eu:
-        assert rel(out[2].cpu().numpy(), g["edge_out"]) < 5e-6
+        errs.append(rel(out[2].cpu().numpy(), g["edge_out"]))
     else:
         assert len(out) == 2
+    print(name, path, layer.engine, "rel err h/x/e:", ["%.2e" % e for e in errs])
+    assert max(errs) < tol
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("De,att,eu", [(H, True, True), (1, False, False)])
-def test_cuda_layer_matches_oracle_stack(De, att, eu):
+@pytest.mark.parametrize("De,att,eu,engine", [(H, True, True, "fp32"), (H, True, True, "strict"), (1, False, False, "fp32")])
+def test_cuda_layer_matches_oracle_stack(De, att, eu, engine):
     """Three chained layers on a ragged dense batch (the gcl_full_* stack of sample_AR, edge_denoise.py:293-294):
     dense path == explicit-list path == oracle; the dense path is bit-reproducible."""
     dev = torch.device("cuda", 0)
@@ -141,6 +151,7 @@ def test_cuda_layer_matches_oracle_stack(De, att, eu):
     ho, xo, eo = h, x, e
     for li in range(3):
         layer, w = make_layer("stack%d" % li, De, att, eu, dev)
+        layer.engine = engine
         od = layer.forward_dense(hd, xd, ed, sz, B, N)
         od2 = layer.forward_dense(hd, xd, ed, sz, B, N)
         assert all(torch.equal(a, b) for a, b in zip(od, od2))
@@ -152,9 +163,9 @@ def test_cuda_layer_matches_oracle_stack(De, att, eu):
         if eu:
             ed, el, eo = od[2], ol[2], oo[2]
         for got in ((hd, xd, ed), (hl, xl, el)):
-            assert rel(got[0].cpu().numpy(), ho) < 1e-5
-            assert rel(got[1].cpu().numpy(), xo) < 1e-5
-            assert rel(got[2].cpu().numpy(), eo) < 1e-5
+            assert rel(got[0].cpu().numpy(), ho) < 2e-5
+            assert rel(got[1].cpu().numpy(), xo) < 2e-5
+            assert rel(got[2].cpu().numpy(), eo) < 2e-5
         # padded rows stay exactly zero
         assert float((hd * (1 - T(nm))).abs().max()) == 0.0 and float((xd * (1 - T(nm))).abs().max()) == 0.0
 
@@ -252,13 +263,20 @@ def test_bfs_depth_edges():
 
 
 @pytest.mark.gpu
-def test_sample_ar_cuda_against_reference(golden_dir):
+@pytest.mark.parametrize("engine,tol", [("fp32", 2e-5), ("strict", 3e-4)])
+def test_sample_ar_cuda_against_reference(golden_dir, engine, tol):
     """Edge_denoise.sample_AR on the CUDA path (hd_egcl_forward dense + list, hd_linear_forward) against the four steps
-    recorded from the unmodified reference: identical decisions and adjacency, logits within 2e-5 of max|ref|."""
+    recorded from the unmodified reference: identical decisions and adjacency; logits within 2e-5 of max|ref| with the
+    fp32 dense layers, 3e-4 with the tcgen05 bf16x3 ones (the default; measured 1.0e-4 at the step whose logits reach 15)."""
     dev = torch.device("cuda", 0)
     g = np.load(os.path.join(golden_dir, "sample_ar.npz"))
     from hierdiff_b200 import native
+    model = make_decoder(dev)
+    for i in range(model.n_layers_full):
+        model._modules["gcl_full_%d" % i].engine = engine
     n0 = native.lib().hd_launch_count()
-    out = run_ar_steps(make_decoder(dev), g, dev)
+    out = run_ar_steps(model, g, dev)
     assert native.lib().hd_launch_count() > n0
-    check_ar(out, g, 2e-5)
+    print("sample_AR", engine, "logit rel err per step:",
+          ["%.2e" % rel(o[1], g["node_predict_%d" % k]) for k, o in enumerate(out)])
+    check_ar(out, g, tol)
