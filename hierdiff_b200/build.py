@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libhierdiff_b200.so")
-SOURCES = ["hd_layout.cu", "hd_fp32.cu", "hd_tc.cu", "hd_node.cu", "hd_api.cu", "hd_egcl.cu"]
+SOURCES = ["hd_layout.cu", "hd_fp32.cu", "hd_tc.cu", "hd_node.cu", "hd_api.cu", "hd_egcl.cu", "hd_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC", "-shared",
               "-Xcompiler", "-fvisibility=hidden"]

@@ -250,6 +250,110 @@ class DiffusionQM9(nn.Module):
         self._raise_on_flags(flags)
         return x, h
 
+    # ------------------------------------------------------------------ loss / NLL, forward value only (:530-751)
+    @torch.no_grad()
+    def compute_loss(self, x, h, node_mask, edge_mask, context, t0_always, mol_shape=None, _inject=None):
+        """diffusion_qm9.py:530-673 without gradients: ``x`` / ``h`` are the normalised, CoG-free inputs of ``nll``.
+        Returns ``(loss [B], {'t', 'loss_t', 'error'})``.  The network calls run through the fused EGNN kernels with one
+        ``t`` per molecule, the rest through ``hd_loss_noise_mix`` / ``hd_loss_terms``.  ``_inject`` (tests): dict with
+        ``t_int`` [B,1], the raw draws ``randn`` = [rx, rh(, rx0, rh0)] in the reference's call order and, optionally,
+        ``gamma`` = (gamma_s, gamma_t, gamma_0, gamma_T) recorded elsewhere (the SNR weight exp(gamma_t - gamma_s) - 1
+        amplifies the 1e-4 device-to-device differences of the gamma network a hundredfold)."""
+        return self._loss(torch.cat([x, h.to(x.dtype) * (node_mask != 0)], dim=2), node_mask, edge_mask, context, t0_always,
+                          mol_shape, _inject, 1.0)[1:]
+
+    def _loss(self, xh, node_mask, edge_mask, context, t0_always, mol_shape, inject, norm_x):
+        if mol_shape is not None and mol_shape != xh.shape[1]:
+            raise NotImplementedError("the pocket-conditioned loss (mol_shape < n_nodes) is not built")
+        native.require_cuda(xh)
+        B, N, D = xh.shape
+        F_ = D - self.n_dims
+        dev = xh.device
+        L = native.lib()
+        sizes = self._masks_to_sizes(node_mask, edge_mask)
+        xh = xh.float().contiguous()
+        lowest = 1 if t0_always else 0
+        if inject is not None:
+            t_int = inject["t_int"].to(dev).float().reshape(B, 1)
+            draws = [d.to(dev).float().contiguous() for d in inject["randn"]]
+        else:
+            t_int = torch.randint(lowest, self.T + 1, size=(B, 1), device=dev).float()    # :544-545
+            draws = None
+        s, t = (t_int - 1) / self.T, t_int / self.T
+        flat = lambda g: g.reshape(-1).float().contiguous()
+        gamma_s, gamma_t = flat(self.gamma(s)), flat(self.gamma(t))
+        zeros, ones = torch.zeros(B, 1, device=dev), torch.ones(B, 1, device=dev)
+        gamma_0, gamma_T = flat(self.gamma(zeros)), flat(self.gamma(ones))
+        if inject is not None and "gamma" in inject:
+            gamma_s, gamma_t, gamma_0, gamma_T = (flat(g.to(dev)) for g in inject["gamma"])
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        P, st = native.ptr, native.stream_ptr
+
+        def noisy(gamma, rx, rh):
+            eps, z = torch.empty_like(xh), torch.empty_like(xh)
+            with torch.cuda.device(dev):
+                native.check(L.hd_combine_noise(P(rx), P(rh), P(sizes), B, N, F_, P(eps), st()), "hd_combine_noise")
+                native.check(L.hd_loss_noise_mix(P(xh), P(eps), P(gamma), P(sizes), B, N, F_, P(z), P(flags), st()),
+                             "hd_loss_noise_mix")
+            return eps, z
+
+        rx, rh = (draws[0], draws[1]) if draws else self._draw(B, N, dev)
+        eps_t, z_t = noisy(gamma_t, rx, rh)
+        net_t = self.dynamics.forward_sizes(t, z_t, sizes, flags=flags, context=context)
+        eps_0 = z_0 = net_0 = None
+        if t0_always:                                                                     # :617-640
+            rx0, rh0 = (draws[2], draws[3]) if draws else self._draw(B, N, dev)
+            eps_0, z_0 = noisy(gamma_0, rx0, rh0)
+            net_0 = self.dynamics.forward_sizes(zeros, z_0, sizes, flags=flags, context=context)
+        cfg = native.HdLossConfig()
+        cfg.T, cfg.t0_always = int(self.T), int(bool(t0_always))
+        cfg.l2_training = int(self.training and self.loss_type == "l2")
+        cfg.int_nf, cfg.cont_nf = (5, 3) if self.node_coarse_type == "prop" else (3, 0)   # :462-467
+        cfg.norm_x, cfg.norm_int, cfg.bias_int = float(norm_x), float(self.norm_values[2]), float(self.norm_biases[2])
+        nll, loss, error = (torch.empty(B, device=dev) for _ in range(3))
+        with torch.cuda.device(dev):
+            native.check(L.hd_loss_terms(cfg, P(xh), P(z_t), P(eps_t), P(net_t), P(z_0), P(eps_0), P(net_0), P(flat(t_int)),
+                                         P(gamma_s), P(gamma_t), P(gamma_0), P(gamma_T), P(sizes), B, N, F_, P(nll), P(loss),
+                                         P(error), None, st()), "hd_loss_terms")
+        self._raise_on_flags(flags)
+        return nll, loss, {"t": t_int.squeeze(), "loss_t": loss.squeeze(), "error": error.squeeze()}
+
+    @torch.no_grad()
+    def nll(self, x, h, node_mask=None, edge_mask=None, context=None, mol_shape=None, _inject=None, _center=False):
+        """diffusion_qm9.py:675-699: normalise, then one network call (training) or two (eval); returns -log p(x, h) [B]."""
+        native.require_cuda(x)
+        B, N, _ = x.shape
+        sizes = self._masks_to_sizes(node_mask, edge_mask)
+        F_ = h.shape[2]
+        xh = torch.empty(B, N, self.n_dims + F_, device=x.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(native.lib().hd_loss_prepare(
+                native.ptr(x.float().contiguous()), native.ptr(h.float().contiguous()), native.ptr(sizes), B, N, F_,
+                float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]), int(_center),
+                native.ptr(xh), native.ptr(flags), native.stream_ptr()), "hd_loss_prepare")
+        self._raise_on_flags(flags)
+        return self._loss(xh, node_mask, edge_mask, context, not self.training, mol_shape, _inject, self.norm_values[0])[0]
+
+    @torch.no_grad()
+    def forward(self, batch, _inject=None):
+        """diffusion_qm9.py:701-751 (the value ``validation_step`` / ``test_step`` return): {'loss': mean NLL}."""
+        if self.pocket:
+            raise NotImplementedError("the pocket-conditioned loss is not built")
+        x, node_mask, edge_mask, h = batch["positions"], batch["atom_mask"], batch["edge_mask"], batch["node_feature"]
+        context = batch["context"] if self.cfg.dynamics.context_node_nf > 0 else None
+        return {"loss": self.nll(x, h, node_mask, edge_mask, context=context, _inject=_inject, _center=True).mean(0)}
+
+    def validation_step(self, batch, batch_idx):
+        return self.forward(batch)
+
+    def test_step(self, batch, batch_idx):
+        return self.forward(batch)
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training needs the backward kernels, which are not built; forward() gives the "
+                                  "objective's value")
+
     # ------------------------------------------------------------------ the sampler
     def mark_weights_changed(self):
         """Call after writing parameters through ``.data`` (which does not bump autograd versions), e.g.

@@ -20,7 +20,7 @@ FLAG_NAN = 1
 FLAG_COG = 2
 FLAG_MASK = 4
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class HdConfig(ctypes.Structure):
@@ -36,6 +36,13 @@ class HdEgclConfig(ctypes.Structure):
     """``hd_egcl_config`` (stage-2 E_GCL hyper-parameters, reference ROOT models/egnn/gcl.py:18)."""
     _fields_ = [("hidden_nf", ctypes.c_int32), ("edges_in_d", ctypes.c_int32), ("attention", ctypes.c_int32),
                 ("tanh", ctypes.c_int32), ("coords_range", ctypes.c_float), ("edge_update", ctypes.c_int32)]
+
+
+class HdLossConfig(ctypes.Structure):
+    """``hd_loss_config`` (diffusion_qm9.py:530-673)."""
+    _fields_ = [("T", ctypes.c_int32), ("t0_always", ctypes.c_int32), ("l2_training", ctypes.c_int32),
+                ("int_nf", ctypes.c_int32), ("cont_nf", ctypes.c_int32), ("norm_x", ctypes.c_float),
+                ("norm_int", ctypes.c_float), ("bias_int", ctypes.c_float)]
 
 
 class NativeError(RuntimeError):
@@ -75,6 +82,9 @@ SIGNATURES = {
     "hd_sampler_step": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _I, _P]),
     "hd_sampler_final": (_I, [_CFG, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P,
                               _I, _P]),
+    "hd_loss_prepare": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P]),
+    "hd_loss_noise_mix": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "hd_loss_terms": (_I, [ctypes.POINTER(HdLossConfig)] + [_P] * 13 + [_I, _I, _I, _P, _P, _P, _P, _P]),
     "hd_linear_forward": (_I, [_P, _L, _I, _P, _P, _I, _I, _P, _P]),
     "hd_egcl_weight_count": (_L, [_ECFG]),
     "hd_egcl_workspace_bytes": (_L, [_ECFG, _L, _L]),

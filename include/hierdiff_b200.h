@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 8
+#define HD_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -248,6 +248,39 @@ HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const 
                                const float* edge_mask, const float* node_mask, const int32_t* sizes, int32_t B, int32_t N,
                                int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out, float* edge_out,
                                void* workspace, int32_t engine, hd_stream_t stream);
+
+/* ---- forward value of the diffusion loss / NLL: the glue of DiffusionQM9.forward -> nll ->
+ * compute_loss (train_module/diffusion_qm9.py:701-751, :675-699, :530-673) around the network calls (hd_dynamics_forward
+ * with one t per molecule).  No gradients - the validation / test value and the training objective's forward value.
+ * hd_loss_prepare:   xh [B,N,3+F] = [ (x - CoG) / norm_x | (h - bias_h) / norm_h ] on the real nodes, 0 elsewhere
+ *                    (forward :726, normalize :165-172); center = 0 skips the CoG removal; HD_FLAG_MASK as the reference's
+ *                    assert (models/utils.py:47-50).
+ * hd_loss_noise_mix: z = alpha(gamma[b]) * xh + sigma(gamma[b]) * eps (:573, :631); HD_FLAG_COG as :574's assert.
+ * hd_loss_terms:     per molecule: error = sum (eps - net)^2 (:250-258), SNR weight (:588-593), kl_prior (:206-234), the
+ *                    constants (:260-289), -log p(x,h|z0) (:460-528, from the t = 0 call when t0_always, else from the same
+ *                    call for the molecules that drew t = 0) and their combination (:617-668); nll = loss - delta_log_px
+ *                    (:694-697).  t_int / gamma_* are [B]; z_0 / eps_0 / net_0 may be NULL unless t0_always;
+ *                    terms (optional) [B][4] = {kl_prior, estimator term, constants, L0}. */
+typedef struct {
+  int32_t T;            /* timesteps */
+  int32_t t0_always;    /* eval: separate t = 0 network call (:617-640) */
+  int32_t l2_training;  /* self.training and loss_type == 'l2' (:253, :588, :603, :657, :683) */
+  int32_t int_nf;       /* integer-valued feature columns (5 'prop' / 3 'elem', :462-467) */
+  int32_t cont_nf;      /* continuous feature columns (3 / 0) */
+  float norm_x;         /* norm_values[0] */
+  float norm_int;       /* norm_values[2] */
+  float bias_int;       /* norm_biases[2] */
+} hd_loss_config;
+HD_API int32_t hd_loss_prepare(const float* x, const float* h, const int32_t* sizes, int32_t B, int32_t N, int32_t F,
+                               float norm_x, float norm_h, float bias_h, int32_t center, float* xh, int32_t* flags,
+                               hd_stream_t stream);
+HD_API int32_t hd_loss_noise_mix(const float* xh, const float* eps, const float* gamma, const int32_t* sizes, int32_t B,
+                                 int32_t N, int32_t F, float* z, int32_t* flags, hd_stream_t stream);
+HD_API int32_t hd_loss_terms(const hd_loss_config* cfg, const float* xh, const float* z_t, const float* eps_t,
+                             const float* net_t, const float* z_0, const float* eps_0, const float* net_0,
+                             const float* t_int, const float* gamma_s, const float* gamma_t, const float* gamma_0,
+                             const float* gamma_T, const int32_t* sizes, int32_t B, int32_t N, int32_t F, float* nll,
+                             float* loss, float* error, float* terms, hd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -319,6 +319,66 @@ def case_pocket(name="pocket_l1", n_layers=1, T=6, sizes=(6, 9, 2), P=5, seed=4)
     print(name, "x absmax", float(np.abs(x).max()), "draw shapes", draws[0].shape, draws[1].shape, len(draws))
 
 
+def case_loss(name, n_layers, T, sizes, seed, training, noise_schedule="learned"):
+    """``DiffusionQM9.forward(batch)`` -> ``nll`` -> ``compute_loss`` (diffusion_qm9.py:701-751, :675-699, :530-673)
+    of the unmodified reference on CPU: eval mode (t0_always, two network calls) or training mode (one call), no
+    gradients.  Recorded: the batch, the timesteps drawn, the raw randn draws in call order and the network outputs, so
+    that the CUDA path can be fed the same randomness."""
+    model = make_reference(n_layers, T, noise_schedule=noise_schedule)
+    model.train(training)
+    B, N = len(sizes), max(sizes)
+    g = torch.Generator().manual_seed(seed)
+    node_mask, edge_mask = masks_for(sizes, N)
+    nm = node_mask.float()
+    x = torch.randn(B, N, 3, generator=g) * nm
+    # integer-valued categorical part (5 columns), continuous part (3), as the 'prop' coarse features are laid out
+    h = torch.cat([torch.randint(0, 4, (B, N, 5), generator=g).float(), torch.randn(B, N, 3, generator=g)], 2) * nm
+    batch = {"positions": x.clone(), "atom_mask": node_mask, "edge_mask": edge_mask, "node_feature": h.clone()}
+    draws, nets, ts, gammas = [], [], [], []
+    real_randn, real_randint, real_phi = torch.randn, torch.randint, model.phi
+    hook = model.gamma.register_forward_hook(lambda m, i, o: gammas.append(o.detach().numpy().copy()))
+
+    def rec_randn(*a, **k):
+        out = real_randn(*a, **k)
+        draws.append(out.numpy().copy())
+        return out
+
+    def rec_randint(*a, **k):
+        out = real_randint(*a, **k)
+        ts.append(out.numpy().copy())
+        return out
+
+    def rec_phi(*a, **k):
+        out = real_phi(*a, **k)
+        nets.append(out.detach().numpy().copy())
+        return out
+
+    torch.manual_seed(seed)
+    torch.randn, torch.randint, model.phi = rec_randn, rec_randint, rec_phi
+    try:
+        with torch.no_grad():
+            out = model.forward(batch)
+            # the per-molecule values behind the mean (same draws again)
+            torch.manual_seed(seed)
+            xc = x - (x.sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
+            per_mol = model.nll(xc, h, node_mask, edge_mask.view(B, N * N), context=None, mol_shape=None)
+    finally:
+        torch.randn, torch.randint, model.phi = real_randn, real_randint, real_phi
+        hook.remove()
+    # gamma calls of compute_loss in order (:562-563, :272, :287, :214[, :623]): s, t, zeros, zeros, ones[, zeros]
+    k = len(draws) // 2
+    rec = dict(x=x.numpy(), h=h.numpy(), sizes=np.array(sizes, np.int32), T=np.int32(T), n_layers=np.int32(n_layers),
+               training=np.int32(training), t_int=ts[0].astype(np.float32), loss=np.float32(out["loss"].item()),
+               nll=per_mol.numpy(), n_net_calls=np.int32(len(nets) // 2), gamma_s=gammas[0], gamma_t=gammas[1],
+               gamma_0=gammas[2], gamma_T=gammas[4])
+    for i in range(k):
+        rec["randn_%d" % i] = draws[i]
+    for i in range(len(nets) // 2):
+        rec["net_%d" % i] = nets[i]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print(name, "loss", float(out["loss"]), "t", ts[0].ravel().tolist(), "draws", [d.shape for d in draws[:k]])
+
+
 def case_gamma():
     model = make_reference(1, 1000)
     t = torch.linspace(0, 1, 41).view(-1, 1)
@@ -345,6 +405,11 @@ def case_nodes_dist():
                         hist_counts=np.array(list(hist.values()), np.int64))
     print("nodes_dist", a[:8])
 
+
+if __name__ == "__main__" and "--loss-only" in sys.argv:
+    case_loss("loss_eval_l2", 2, 1000, [7, 4, 9, 1], 11, training=False)
+    case_loss("loss_train_l1", 1, 3, [6, 9, 2, 5, 8, 3], 13, training=True)      # T = 3: two molecules draw t = 0
+    sys.exit(0)
 
 if __name__ == "__main__":
     torch.set_num_threads(8)

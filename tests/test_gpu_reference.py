@@ -236,3 +236,37 @@ def test_weights_reloaded_after_capture_are_used(tmp_path):
     torch.manual_seed(7)
     xc, _ = c.sample_padded(sizes, dev())
     assert torch.equal(xa3, xc)
+
+
+@pytest.mark.parametrize("training,engine,tol", [(False, "strict", 2e-4), (False, "fp32", 2e-5), (True, "strict", 2e-4)])
+def test_seeded_loss_matches_reference(tmp_path, training, engine, tol):
+    """``forward(batch)`` -> ``nll`` -> ``compute_loss`` (diffusion_qm9.py:701-751), forward value only,
+    against the reference on the same GPU under the same seed: its randint / randn draws and its gamma calls are
+    reproduced by construction (same shapes, same order), nothing is injected."""
+    L, T, sizes = 2, 1000, np.array([7, 4, 9, 1, 12, 6], np.int64)
+    B, N = len(sizes), int(sizes.max())
+    g = torch.Generator().manual_seed(17)
+    nm = torch.from_numpy(np.arange(N)[None, :] < sizes[:, None])
+    em = nm[:, :, None] & nm[:, None, :] & ~torch.eye(N, dtype=torch.bool)[None]
+    x = torch.randn(B, N, 3, generator=g) * nm[:, :, None]
+    h = torch.cat([torch.randint(0, 4, (B, N, 5), generator=g).float(), torch.randn(B, N, 3, generator=g)], 2) * nm[:, :, None]
+    batch = {"positions": x.to(dev()), "atom_mask": nm[:, :, None].to(dev()), "edge_mask": em.to(dev()),
+             "node_feature": h.to(dev())}
+    ref = R.make_reference(L, T).to(dev())
+    ref.train(training)
+    xc = batch["positions"] - (batch["positions"].sum(1, keepdim=True) / nm.sum(1).view(B, 1, 1).to(dev())) * nm[:, :, None].to(dev())
+    with torch.no_grad():
+        torch.manual_seed(3)
+        want = ref.nll(xc, batch["node_feature"], batch["atom_mask"], batch["edge_mask"].view(B, N * N), context=None).cpu().numpy()
+        torch.manual_seed(3)
+        want_mean = float(ref.forward({k: v.clone() for k, v in batch.items()})["loss"])
+    model = make_model(tmp_path, L, timesteps=T, device=dev(), engine=engine)
+    model.train(training)
+    torch.manual_seed(3)
+    got = model.nll(xc, batch["node_feature"], batch["atom_mask"], batch["edge_mask"]).cpu().numpy()
+    torch.manual_seed(3)
+    got_mean = float(model.forward(batch)["loss"])
+    err = float(np.abs(got - want).max() / np.abs(want).max())
+    record(f"loss_{'train' if training else 'eval'}_{engine}", {"per_molecule_rel": err, "mean": got_mean, "mean_ref": want_mean})
+    assert err < tol, (err, got, want)
+    assert abs(got_mean - want_mean) <= tol * float(np.abs(want).max())
