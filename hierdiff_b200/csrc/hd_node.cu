@@ -106,7 +106,8 @@ struct Params2 {
   int tiles_a, tiles_ab;
 };
 
-template <bool STRICT, int NT, bool RAGGED = false>
+// EXT: the stage-2 epilogue modes 4-6 (hd_egcl.cu); the coarse-grained path instantiates the kernel without them
+template <bool STRICT, int NT, bool RAGGED = false, bool EXT = false>
 __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   using S = Smem<STRICT, NT>;
   const int which = (int)blockIdx.y < pp.tiles_a ? 0 : ((int)blockIdx.y < pp.tiles_ab ? 1 : 2);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
         }
       }
       const int col = ct * NT + oc4;
-      if (p.mode >= 4) {
+      if (EXT && p.mode >= 4) {
         if (p.mode == 5) {
           const int j = row % p.N, i = (row / p.N) % p.N, n = p.sizes[row / (p.N * p.N)];
           const float mk = (i < n && j < n && i != j) ? 1.f : 0.f;
@@ -352,15 +353,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) linear_tc_k(const Params2 pp) {
   HD_STAMP(10, tid == 32 * NPROD);
 }
 
-template <bool STRICT, int NT, bool RAGGED = false>
+template <bool STRICT, int NT, bool RAGGED = false, bool EXT = false>
 static int launch2(const Params& a, int n_out_a, const Params* b, int n_out_b, cudaStream_t st,
                    const Params* c3 = nullptr, int n_out_c = 0) {
-  if constexpr (!RAGGED) {
+  if constexpr (!RAGGED && !EXT) {
     if (a.ragged) return launch2<STRICT, NT, true>(a, n_out_a, b, n_out_b, st, c3, n_out_c);
   }
   using S = Smem<STRICT, NT>;
   static bool configured = false;
-  auto kern = linear_tc_k<STRICT, NT, RAGGED>;
+  auto kern = linear_tc_k<STRICT, NT, RAGGED, EXT>;
   if (!configured) {
     HD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
@@ -420,6 +421,9 @@ int linear_tc(const FwdCtx& c, const float* X1, int ld1, int K1, const float* X2
     set_error("linear_tc: unsupported shape K1=%d K2=%d n_out=%d tile_n=%d", K1, K2, n_out, tile_n);
     return HD_E_INVALID;
   }
+#ifdef HD_EXP_SKIP_NODE   // timing experiment only (scripts/step_ablation.sh): what the node launches cost inside the chain
+  return HD_OK;
+#endif
   const lin::Params p = make_params(c, X1, ld1, K1, X2, ld2, K2, w_hi, w_lo, bias, Y, ldy, mode, resid);
   if (tile_n == 128) return strict ? lin::launch<true, 128>(p, n_out, c.stream) : lin::launch<false, 128>(p, n_out, c.stream);
   return strict ? lin::launch<true, 64>(p, n_out, c.stream) : lin::launch<false, 64>(p, n_out, c.stream);
@@ -440,7 +444,8 @@ int linear_tc_rows(cudaStream_t st, int rows, const float* X1, int ld1, int K1, 
   p.w_hi = w_hi; p.w_lo = w_lo; p.bias = bias; p.Y = Y; p.ldy = ldy; p.rows = rows; p.grid_rows = rows; p.mode = mode;
   p.resid = resid ? resid : Y; p.sizes = sizes; p.N = N; p.B = 0; p.ragged = 0;
   p.s = s; p.ws = ws; p.ab = ab;
-  return strict ? lin::launch<true, 128>(p, n_out, st) : lin::launch<false, 128>(p, n_out, st);
+  return strict ? lin::launch2<true, 128, false, true>(p, n_out, nullptr, 0, st)
+                : lin::launch2<false, 128, false, true>(p, n_out, nullptr, 0, st);
 }
 
 // node_mlp.2 (+ residual, mask) -> h_out and, in the same launch, the next sub-layer's A|B pre-projection computed
@@ -450,6 +455,9 @@ int linear_tc_v2_and_preproject(const FwdCtx& c, const float* hid, const float* 
                                 const void* v2_lo, const float* c2, const void* m_hi, const void* m_lo,
                                 const float* bm, float* ab, bool strict, const void* m2_hi, const void* m2_lo,
                                 const float* bm2, float* ab2) {
+#ifdef HD_EXP_SKIP_NODE
+  return HD_OK;
+#endif
   const lin::Params a = make_params(c, hid, H, H, nullptr, 0, 0, v2_hi, v2_lo, c2, h_out, H, 2, h);
   const lin::Params b = make_params(c, h, H, H, hid, H, H, m_hi, m_lo, bm, ab, 2 * H, 3, nullptr);
   if (m2_hi) {

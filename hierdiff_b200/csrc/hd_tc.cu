@@ -1040,6 +1040,9 @@ static int edge_launch(const FwdCtx& c, int si, const float* x, const float* x0,
   auto F = [&](int64_t off) { return reinterpret_cast<const float*>(c.packed + off); };
   int rc = ensure_plan(c);
   if (rc) return rc;
+#ifdef HD_EXP_SKIP_EDGE   // timing experiment only (scripts/step_ablation.sh)
+  return HD_OK;
+#endif
   tc::Params p{};
   p.a_img = reinterpret_cast<const float*>(c.ws + (use_ab2 ? c.W.ab2 : c.W.ab));
   p.kc_stride = (int64_t)c.B * c.N * 16;

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libhierdiff_b200.so")
+# HD_LIB_PATH: an alternative build of the same library (timing experiments: scripts/step_ablation.sh)
+LIB_PATH = os.environ.get("HD_LIB_PATH") or os.path.join(_HERE, "_lib", "libhierdiff_b200.so")
 
 ENGINE_FP32 = 0
 ENGINE_TC_STRICT = 1

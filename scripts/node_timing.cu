@@ -28,7 +28,7 @@ int main() {
     lin::Params p{};
     p.X1 = X; p.X2 = X + 256; p.ld1 = 512; p.ld2 = 512; p.K1 = K1; p.K2 = K2;
     p.w_hi = whi; p.w_lo = wlo; p.bias = bias; p.Y = Y; p.ldy = n_out; p.rows = rows; p.mode = mode;
-    p.resid = Y; p.sizes = sizes; p.N = 40;
+    p.resid = Y; p.sizes = sizes; p.N = 40; p.grid_rows = rows; p.B = 64;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int it = 0; it < 3; ++it) {
