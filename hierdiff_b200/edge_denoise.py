@@ -105,12 +105,15 @@ class Edge_denoise(nn.Module):
     def _walk_depths(self, layer, h, x, depth_lists, node_mask, bs, n):
         """:339-347 / :389-398: the self edge of every molecule's node 0 first, then one layer call per BFS depth."""
         circle = [[i * n, i * n] for i in range(bs)]
-        for pairs in [circle] + depth_lists:
-            if not pairs:
-                continue
-            e = torch.tensor(pairs, device=h.device, dtype=torch.long).T.contiguous()
-            radial = ((x[e[0]] - x[e[1]]) ** 2).sum(1, keepdim=True)
-            h, x = layer(h, [e[0], e[1]], x, edge_attr=radial, node_mask=node_mask)
+        depths = [pairs for pairs in [circle] + depth_lists if pairs]
+        # one host-to-device copy for every depth's edge list (a small pageable copy costs ~0.2 ms each)
+        flat = torch.tensor([p for pairs in depths for p in pairs], dtype=torch.long).T.contiguous().to(h.device)
+        at = 0
+        for pairs in depths:
+            row, col = flat[0, at:at + len(pairs)], flat[1, at:at + len(pairs)]
+            at += len(pairs)
+            radial = ((x[row] - x[col]) ** 2).sum(1, keepdim=True)
+            h, x = layer(h, [row, col], x, edge_attr=radial, node_mask=node_mask)
         return h, x
 
     @staticmethod
@@ -180,8 +183,9 @@ class Edge_denoise(nn.Module):
         any_edge = adj_np.sum() > 0
         if any_edge:
             b_i, r_i, c_i = np.nonzero((adj_np != 0) & size_corner)
-            fe = [torch.from_numpy(b_i * n + r_i).to(dev), torch.from_numpy(b_i * n + c_i).to(dev)]
-            ef = edge_feat4[torch.from_numpy(b_i).to(dev), torch.from_numpy(r_i).to(dev), torch.from_numpy(c_i).to(dev), :]
+            idx = torch.from_numpy(np.stack([b_i * n + r_i, b_i * n + c_i, b_i, r_i, c_i])).to(dev)   # one copy
+            fe = [idx[0], idx[1]]
+            ef = edge_feat4[idx[2], idx[3], idx[4], :]
             for i in range(self.n_layers_focal):
                 h, x, ef = self._modules["gcl_focal_%d" % i](h, fe, x, edge_attr=ef, node_mask=node_mask)
             score = _head(self.focal_predict, torch.cat([h, val], dim=1)).reshape(bs, n).cpu().numpy()

@@ -67,7 +67,7 @@ class E_GCL(nn.Module):
 
     def flat_weights(self, device):
         """The parameters in state_dict order as one fp32 device buffer (rebuilt when a parameter changes)."""
-        params = list(self.state_dict(keep_vars=True).values())
+        params = list(self.parameters())     # registration order = state_dict order (the layer has no buffers)
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
         if self._flat is None or self._flat[0] != key:
             flat = torch.cat([p.detach().reshape(-1).to(device=device, dtype=torch.float32) for p in params])
