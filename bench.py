@@ -38,8 +38,9 @@ T_STEPS, HIDDEN = 1000, 256
 METRIC = "molecules/sec (batch x N nodes, T=1000)"
 UNIT = "molecules/s"
 SWEEP_N = [16, 24, 32, 40, 56]
-# MUFU operations the edge kernel issues per edge-channel (two SiLU evaluations): strict = 2 x (ex2 + rcp), fast = 2 x tanh
-MUFU_PER_EDGE_CHANNEL = {"strict": 4.0, "fast": 2.0, "fp32": 0.0}
+# MUFU operations the edge kernel issues per edge-channel (two SiLU evaluations): strict = 2 x (ex2 + half a rcp: one
+# reciprocal serves a pair of elements), fast = 2 x tanh
+MUFU_PER_EDGE_CHANNEL = {"strict": 3.0, "fast": 2.0, "fp32": 0.0}
 
 
 class Workload:
@@ -518,6 +519,14 @@ def edge_kernel_roofline(model, loop, engine, B, N, iters=20):
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_name, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "tensor_passes": {"strict": 3, "fast": 1, "fp32": 0}[engine],
+            # context for `frac` (which counts the algorithmic one-pass FLOPs): the bf16x3 strict engine issues three
+            # tcgen05 passes per product, so its tensor pipe is busy for passes x achieved
+            "tensor_issued": ({"tflops": achieved * {"strict": 3, "fast": 1}[engine],
+                               "frac_of_peak": achieved * {"strict": 3, "fast": 1}[engine] / peak,
+                               "note": "profiles/r2_notes.md: with the operand producers switched off the strict kernel "
+                                       "takes 39.8 us (6 tile slots x 4.55 us at the measured bf16 rate + fill/drain), "
+                                       "which caps the one-pass fraction near 0.21"}
+                              if engine in ("strict", "fast") else None),
             "sfu": {"mufu_ops_per_launch": mufu, "floor_ms": sfu_floor_ms,
                     "frac": (sfu_floor_ms / ms) if mufu else None,
                     "note": "co-bound: SiLU on every edge-channel twice; 16 MUFU lanes/clk/SM at sm_max_mhz"},
