@@ -215,6 +215,67 @@ __global__ void __launch_bounds__(256) gemm_k(const GemmArgs a) {
   }
 }
 
+// The same product for FEW rows (the explicit edge lists and the prediction heads of sample_AR: tens to hundreds of
+// rows, where the 64 x 64 tiles above leave the GPU to 4-8 CTAs that each walk all of K): a CTA owns 32 rows x 8 output
+// columns, a warp one column; the lanes split K (coalesced weight reads, the 32 x 128 activation chunk in shared memory)
+// and a shuffle transpose-reduction leaves lane m with the sum of row m.
+constexpr int GS_ROWS = 32, GS_COLS = 8, GS_KC = 128;
+__global__ void __launch_bounds__(32 * GS_COLS) gemm_small_k(const GemmArgs a) {
+  __shared__ float sx[GS_ROWS][GS_KC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * GS_ROWS, n = blockIdx.y * GS_COLS + warp;
+  const bool col_ok = n < a.Nout;
+  const int K = a.K1 + a.K2;
+  float acc[GS_ROWS];
+#pragma unroll
+  for (int r = 0; r < GS_ROWS; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += GS_KC) {
+    for (int idx = threadIdx.x; idx < GS_ROWS * GS_KC; idx += 32 * GS_COLS) {
+      const int r = idx / GS_KC, k = k0 + idx % GS_KC, m = m0 + r;
+      float v = 0.f;
+      if (m < a.M && k < K) v = k < a.K1 ? a.X1[(int64_t)m * a.ld1 + k] : a.X2[(int64_t)m * a.ld2 + (k - a.K1)];
+      sx[r][idx % GS_KC] = v;
+    }
+    __syncthreads();
+    float w[GS_KC / 32];
+#pragma unroll
+    for (int j = 0; j < GS_KC / 32; ++j) {
+      const int k = k0 + lane + 32 * j;
+      w[j] = (col_ok && k < K) ? a.W[(int64_t)n * a.ldw + (k < a.K1 ? a.c1 + k : a.c2 + (k - a.K1))] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < GS_ROWS; ++r)
+#pragma unroll
+      for (int j = 0; j < GS_KC / 32; ++j) acc[r] = fmaf(sx[r][lane + 32 * j], w[j], acc[r]);
+    __syncthreads();
+  }
+  // transpose-reduction: after the five halving steps lane m holds sum over lanes of acc[m]
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int r = 0; r < step; ++r) {
+      const float send = up ? acc[r] : acc[r + step], keep = up ? acc[r + step] : acc[r];
+      acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  const int m = m0 + lane;   // lane's row: bit k of the lane index selected the upper half at the step of size 2^k
+  if (!col_ok || m >= a.M) return;
+  float v = acc[0];
+  if (a.bias) v += a.bias[n];
+  if (a.s) v = fmaf(a.s[m], a.W[(int64_t)n * a.ldw + a.cs], v);
+  if (a.act == 1) v = silu_acc(v);
+  if (a.resid) v += a.resid[(int64_t)m * a.ldy + n];
+  if (a.mask_mode == 1) v *= node_get(a.ns, m);
+  if (a.mask_mode == 2) {
+    int row, col;
+    float mk = edge_get(a.es, m, row, col);
+    if (a.mask_twice) mk *= mk;
+    v *= mk;
+  }
+  a.Y[(int64_t)m * a.ldy + n] = v;
+}
+
 // per edge: radial, m1 = SiLU(A_row + B_col + radial * w_r + (P or sum_d e_d * w_e,d))     one CTA of 128 threads per edge
 __global__ void mes1_k(const float* __restrict__ ab, const float* __restrict__ pe, const float* __restrict__ edge_attr,
                        int De, const float* __restrict__ x, const float* __restrict__ w0, int ldw, int col_r,
@@ -341,6 +402,12 @@ __global__ void radial_dense_k(const float* __restrict__ x, int N, int64_t E, fl
 
 static int gemm(cudaStream_t st, const GemmArgs& a) {
   if (a.M < 1) return HD_OK;
+  if (a.M <= 2048) {   // few rows: many small CTAs instead of a handful of 64 x 64 tiles
+    dim3 grid((a.M + GS_ROWS - 1) / GS_ROWS, (a.Nout + GS_COLS - 1) / GS_COLS);
+    gemm_small_k<<<grid, 32 * GS_COLS, 0, st>>>(a);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+  }
   dim3 grid((a.M + 63) / 64, (a.Nout + 63) / 64);
   gemm_k<<<grid, 256, 0, st>>>(a);
   HD_CHECK_LAUNCH();
