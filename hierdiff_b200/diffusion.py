@@ -162,17 +162,22 @@ class DiffusionQM9(nn.Module):
             raise AssertionError("Mean is not zero")                          # models/utils.py:65-70
         return v
 
-    def _draw(self, B, N, device):
-        """The two raw draws of sample_combined_position_feature_noise, in the reference's order (:449-454)."""
-        rx = torch.randn((B, N, self.n_dims), device=device)
-        rh = torch.randn((B, N, self.in_node_nf), device=device)
+    def _draw(self, B, N, device, fix_noise=False):
+        """The two raw draws of sample_combined_position_feature_noise, in the reference's order (:449-454).
+        ``fix_noise`` (en_diffusion.py:322-323, :639-642): batch size 1, broadcast over the molecules."""
+        b = 1 if fix_noise else B
+        rx = torch.randn((b, N, self.n_dims), device=device)
+        rh = torch.randn((b, N, self.in_node_nf), device=device)
+        if fix_noise:
+            rx, rh = rx.expand(B, -1, -1).contiguous(), rh.expand(B, -1, -1).contiguous()
         return rx, rh
 
-    def sample_combined_position_feature_noise(self, n_samples, n_nodes, node_mask):
-        """diffusion_qm9.py:445-456."""
+    def sample_combined_position_feature_noise(self, n_samples, n_nodes, node_mask, fix_noise=False):
+        """diffusion_qm9.py:445-456 (``fix_noise``: the reference's call with n_samples = 1, whose result broadcasts
+        against the [B, N, 1] mask)."""
         native.require_cuda(node_mask)
         sizes = sizes_from_node_mask(node_mask, n_samples, n_nodes)
-        rx, rh = self._draw(n_samples, n_nodes, node_mask.device)
+        rx, rh = self._draw(n_samples, n_nodes, node_mask.device, fix_noise)
         z = torch.empty(n_samples, n_nodes, self.n_dims + self.in_node_nf, device=node_mask.device)
         with torch.cuda.device(z.device):
             native.check(native.lib().hd_combine_noise(native.ptr(rx), native.ptr(rh), native.ptr(sizes), n_samples,
@@ -182,15 +187,11 @@ class DiffusionQM9(nn.Module):
 
     def sample_normal(self, mu, sigma, node_mask, fix_noise=False):
         """diffusion_qm9.py:438-442."""
-        if fix_noise:
-            raise NotImplementedError("fix_noise=True is not built")
-        return mu + sigma * self.sample_combined_position_feature_noise(mu.size(0), mu.size(1), node_mask)
+        return mu + sigma * self.sample_combined_position_feature_noise(mu.size(0), mu.size(1), node_mask, fix_noise)
 
     @torch.no_grad()
     def sample_p_zs_given_zt(self, s, t, zt, node_mask, edge_mask, context, fix_noise=False, mol_shape=None):
         """diffusion_qm9.py:312-345: one ancestral step, eager (per-molecule schedule rows like the reference)."""
-        if fix_noise:
-            raise NotImplementedError("fix_noise is not built")
         B, N, _ = zt.shape
         L = native.lib()
         gamma_s = self.gamma(s).reshape(-1).float().contiguous()
@@ -210,7 +211,7 @@ class DiffusionQM9(nn.Module):
         else:
             sizes = self._masks_to_sizes(node_mask, edge_mask)
             eps = self.dynamics.forward_sizes(t, zt, sizes, flags=flags, context=context)
-        rx, rh = self._draw(B, N, zt.device)
+        rx, rh = self._draw(B, N, zt.device, fix_noise)
         zs = torch.empty_like(zt)
         with torch.cuda.device(zt.device):
             st = native.stream_ptr()
@@ -225,8 +226,6 @@ class DiffusionQM9(nn.Module):
     @torch.no_grad()
     def sample_p_xh_given_z0(self, z0, node_mask, edge_mask, context, fix_noise=False, _norm=None):
         """diffusion_qm9.py:294-310.  ``_norm``: (norm_x, norm_h, bias_h) override used by the EDM adapter."""
-        if fix_noise:
-            raise NotImplementedError("fix_noise is not built")
         B, N, _ = z0.shape
         L = native.lib()
         sizes = self._masks_to_sizes(node_mask, edge_mask)
@@ -236,7 +235,7 @@ class DiffusionQM9(nn.Module):
         flags = torch.zeros(1, dtype=torch.int32, device=z0.device)
         z0 = z0.contiguous().float()
         eps = self.dynamics.forward_sizes(zeros, z0, sizes, flags=flags, context=context)
-        rx, rh = self._draw(B, N, z0.device)
+        rx, rh = self._draw(B, N, z0.device, fix_noise)
         x = torch.empty(B, N, self.n_dims, device=z0.device)
         h = torch.empty(B, N, self.in_node_nf, device=z0.device)
         nx, nh, bh = _norm if _norm is not None else (self.norm_values[0], self.norm_values[1], self.norm_biases[1])

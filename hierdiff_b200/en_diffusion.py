@@ -70,16 +70,22 @@ class EnVariationalDiffusion(DiffusionQM9):
     @torch.no_grad()
     def sample(self, n_samples, n_nodes, node_mask, edge_mask, context, fix_noise=False):
         """en_diffusion.py:634-667: ``(x [B,N,3], h {'integer','categorical'})`` on ``node_mask``'s device."""
-        if fix_noise:
-            raise NotImplementedError("fix_noise is not built")
+        x, z_h, node_mask = self._run_chain(n_samples, n_nodes, node_mask, edge_mask, context, fix_noise, None)
+        return self._finish(x, z_h, node_mask)
+
+    def _run_chain(self, n_samples, n_nodes, node_mask, edge_mask, context, fix_noise, on_step):
         native.require_cuda(node_mask)
         device = node_mask.device
         node_mask = node_mask.reshape(n_samples, n_nodes, 1)
         sizes = self._masks_to_sizes(node_mask, edge_mask)
         loop = self.sampling_loop(n_samples, n_nodes, device)
-        x, z_h, flags = loop.run(sizes.cpu(), context=context, norm=(self.norm_values[0], 1.0, 0.0))
+        x, z_h, flags = loop.run(sizes.cpu(), context=context, norm=(self.norm_values[0], 1.0, 0.0), fix_noise=fix_noise,
+                                 on_step=on_step)
         x, z_h = x.clone(), z_h.clone()
         self._raise_on_flags(flags)
+        return x, z_h, node_mask
+
+    def _finish(self, x, z_h, node_mask):
         h = self._to_edm_h(z_h, node_mask != 0)
         nm = (node_mask != 0).to(x.dtype)
         x = x * nm
@@ -88,3 +94,32 @@ class EnVariationalDiffusion(DiffusionQM9):
             print(f"Warning cog drift with error {max_cog:.3f}. Projecting the positions down.")
             x = x - (x.sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
         return x, h
+
+    def unnormalize_z(self, z, node_mask):
+        """en_diffusion.py:243-252 (with :318-326): [x * nv0 | (h_cat * nv1 + nb1) * mask | (h_int * nv2 + nb2) * mask]."""
+        nm = (node_mask != 0).to(z.dtype)
+        nc = self.num_classes
+        x = z[:, :, :self.n_dims] * self.norm_values[0]
+        h_cat = (z[:, :, self.n_dims:self.n_dims + nc] * self.norm_values[1] + self.norm_biases[1]) * nm
+        parts = [x, h_cat]
+        if self.include_charges:
+            parts.append((z[:, :, self.n_dims + nc:self.n_dims + nc + 1] * self.norm_values[2] + self.norm_biases[2]) * nm)
+        return torch.cat(parts, dim=2)
+
+    @torch.no_grad()
+    def sample_chain(self, n_samples, n_nodes, node_mask, edge_mask, context, keep_frames=None):
+        """en_diffusion.py:669-712: the chain with ``keep_frames`` intermediate states, flattened to
+        [n_samples * keep_frames, n_nodes, 3 + in_node_nf]; frame 0 is the final sample.  The steps are issued one by one
+        (no captured graph) so that the frames can be copied out between them."""
+        keep_frames = self.T if keep_frames is None else keep_frames
+        assert keep_frames <= self.T
+        nm3 = node_mask.reshape(n_samples, n_nodes, 1)
+        chain = torch.zeros((keep_frames, n_samples, n_nodes, self.n_dims + self.in_node_nf), device=node_mask.device)
+
+        def keep(s, z):
+            chain[(s * keep_frames) // self.T] = self.unnormalize_z(z, nm3)
+
+        x, z_h, nm3 = self._run_chain(n_samples, n_nodes, node_mask, edge_mask, context, False, keep)
+        x, h = self._finish(x, z_h, nm3)
+        chain[0] = torch.cat([x, h["categorical"].to(x.dtype), h["integer"].to(x.dtype)], dim=2)   # :706-707
+        return chain.view(n_samples * keep_frames, n_nodes, -1)

@@ -85,6 +85,10 @@ class SamplingLoop:
         self.z = torch.zeros(B, N, D, **f32)
         self.rx = torch.zeros(B, N, 3, **f32)
         self.rh = torch.zeros(B, N, self.F, **f32)
+        # fix_noise (en_diffusion.py:639-642, :322-323): every draw has batch size 1 and is broadcast over the molecules
+        self.fix_noise = False
+        self.rx1 = torch.zeros(1, N, 3, **f32)
+        self.rh1 = torch.zeros(1, N, self.F, **f32)
         self.flags = torch.zeros(1, dtype=torch.int32, device=device)
         self.sizes = torch.full((B,), N, dtype=torch.int32, device=device)
         C = model.dynamics.context_node_nf
@@ -104,7 +108,18 @@ class SamplingLoop:
 
     @property
     def graph(self):
-        return self._graphs.get((self.ragged, self.live_rows))
+        return self._graphs.get((self.ragged, self.live_rows, self.fix_noise))
+
+    def _draw(self):
+        """The two raw draws of a step, in the reference's order and shapes (diffusion_qm9.py:449-454)."""
+        if self.fix_noise:
+            self.rx1.normal_()
+            self.rh1.normal_()
+            self.rx.copy_(self.rx1.expand_as(self.rx))
+            self.rh.copy_(self.rh1.expand_as(self.rh))
+        else:
+            self.rx.normal_()
+            self.rh.normal_()
 
     @staticmethod
     def ragged_rows_pay(sizes_host, B, N):
@@ -129,8 +144,7 @@ class SamplingLoop:
 
     def _step(self):
         cfg, packed, ws, engine, live = self._common()
-        self.rx.normal_()
-        self.rh.normal_()
+        self._draw()
         native.check(native.lib().hd_sampler_step(
             cfg, packed, native.ptr(self.z), native.ptr(self.rx), native.ptr(self.rh), native.ptr(self.table.t),
             native.ptr(self.table.sched), self.B, self.table.T, native.ptr(self.context), self.C,
@@ -141,8 +155,7 @@ class SamplingLoop:
         """``norm``: (norm_x, norm_h, bias_h) of ``unnormalize`` (diffusion_qm9.py:174-179); default: the model's."""
         m = self.model
         cfg, packed, ws, engine, live = self._common()
-        self.rx.normal_()
-        self.rh.normal_()
+        self._draw()
         nx, nh, bh = norm if norm is not None else (m.norm_values[0], m.norm_values[1], m.norm_biases[1])
         native.check(native.lib().hd_sampler_final(
             cfg, packed, native.ptr(self.z), native.ptr(self.rx), native.ptr(self.rh), native.ptr(self.table.t),
@@ -168,7 +181,7 @@ class SamplingLoop:
         self.flags.copy_(saved[1])
         torch.cuda.synchronize(self.device)
         torch.cuda.set_rng_state(rng, self.device)
-        self._graphs[(self.ragged, self.live_rows)], self.graph_steps = g, k
+        self._graphs[(self.ragged, self.live_rows, self.fix_noise)], self.graph_steps = g, k
 
     def prepare(self, table):
         """Bind the schedule table and (re)capture the graph; not part of a sample's timed region."""
@@ -187,14 +200,17 @@ class SamplingLoop:
             with torch.cuda.device(self.device):
                 self._capture(k)
 
-    def run(self, sizes_host, z_T=None, context=None, norm=None):
-        """Run the whole chain; returns padded (x [B,N,3], h [B,N,F]) on the device and the status word."""
+    def run(self, sizes_host, z_T=None, context=None, norm=None, fix_noise=False, on_step=None):
+        """Run the whole chain; returns padded (x [B,N,3], h [B,N,F]) on the device and the status word.
+        ``fix_noise``: one noise draw per step shared by all molecules.  ``on_step(s, z)``: called after the reverse step
+        that produced z_s (s = T-1 ... 0) - the chain then runs step by step without the captured graph."""
         T = self.table.T
         if (context is None) != (self.context is None):
             raise ValueError("context must be given exactly when the dynamics has context_node_nf > 0")
         sizes_list = sizes_host.tolist() if hasattr(sizes_host, "tolist") else list(sizes_host)
         if len(sizes_list) != self.B or min(sizes_list) < 1 or max(sizes_list) > self.N:
             raise ValueError(f"sizes must be {self.B} values in [1, {self.N}]")
+        self.fix_noise = bool(fix_noise)
         self.ragged = self.ragged_rows_pay(sizes_list, self.B, self.N)
         self.live_rows = -(-int(sum(sizes_list)) // 128) * 128 if self.ragged else 0
         with torch.cuda.device(self.device):
@@ -208,8 +224,7 @@ class SamplingLoop:
             self.flags.zero_()
             if z_T is None:
                 # z_T ~ sample_combined_position_feature_noise (diffusion_qm9.py:361)
-                self.rx.normal_()
-                self.rh.normal_()
+                self._draw()
                 native.check(native.lib().hd_combine_noise(
                     native.ptr(self.rx), native.ptr(self.rh), native.ptr(self.sizes), self.B, self.N, self.F,
                     native.ptr(self.z), native.stream_ptr()), "hd_combine_noise")
@@ -220,13 +235,15 @@ class SamplingLoop:
                 torch.cuda.nvtx.range_push(f"hierdiff.chain B={self.B} N={self.N} T={T}")
             self._begin()
             done = 0
-            if self.graph is not None:
+            if self.graph is not None and on_step is None:
                 while done + self.graph_steps <= T:
                     self.graph.replay()
                     done += self.graph_steps
             while done < T:
                 self._step()
                 done += 1
+                if on_step is not None:
+                    on_step(T - done, self.z)
             if nvtx:
                 torch.cuda.nvtx.range_push("hierdiff.final_decode")
             self._final(norm)

@@ -446,3 +446,44 @@ def test_en_variational_diffusion_adapter(tmp_path):
     zs = edm.sample_p_zs_given_zt(torch.full((4, 1), 0.4, device=dev()), torch.full((4, 1), 0.5, device=dev()),
                                   qm9.sample_combined_position_feature_noise(4, 9, nm), nm, em, None)
     assert zs.shape == (4, 9, 11) and torch.isfinite(zs).all()
+
+
+def test_fix_noise_and_sample_chain(tmp_path):
+    """EnVariationalDiffusion.sample(fix_noise=True) (en_diffusion.py:639-642, :322-323: every draw has batch size 1 and
+    is broadcast) and sample_chain (:669-712).  The reference copy of this class cannot be imported, so the checks are
+    properties: molecules of equal size receive the same noise and end identical; the graph-replayed fix_noise chain
+    equals the step-by-step one; frame 0 of sample_chain is the final sample of the same seed, every kept frame is the
+    unnormalised z_s of its step."""
+    from hierdiff_b200 import EnVariationalDiffusion
+    from hierdiff_b200.utils import masks_from_sizes
+    T = 16
+    qm9 = make_model(tmp_path, 1, timesteps=T, device=dev(), engine="strict")
+    edm = EnVariationalDiffusion(qm9.dynamics, in_node_nf=8, n_dims=3, timesteps=T).to(dev())
+    edm.gamma.load_state_dict(qm9.gamma.state_dict())
+    edm.engine = "strict"
+    sizes = [7, 7, 4, 7]
+    nm, em = masks_from_sizes(sizes, 7, dev())
+    torch.manual_seed(9)
+    x, h = edm.sample(4, 7, nm, em, None, fix_noise=True)
+    assert torch.equal(x[0], x[1]) and torch.equal(x[0], x[3]) and not torch.equal(x[0, :4], x[2, :4])
+    assert torch.equal(h["categorical"][0], h["categorical"][3])
+    # eager per-step API with fix_noise consumes the same stream: z_T, then T steps, then the decode
+    torch.manual_seed(9)
+    z = qm9.sample_combined_position_feature_noise(4, 7, nm, fix_noise=True)
+    for s in reversed(range(T)):
+        z = edm.sample_p_zs_given_zt(torch.full((4, 1), s / T, device=dev()), torch.full((4, 1), (s + 1) / T, device=dev()),
+                                     z, nm, em, None, fix_noise=True)
+    xe, _ = edm.sample_p_xh_given_z0(z, nm, em, None, fix_noise=True)
+    assert torch.allclose(xe * nm, x, rtol=0, atol=2e-5 * float(x.abs().max()))
+    # sample_chain
+    torch.manual_seed(11)
+    xs, hs = edm.sample(4, 7, nm, em, None)
+    torch.manual_seed(11)
+    chain = edm.sample_chain(4, 7, nm, em, None, keep_frames=4)
+    assert chain.shape == (16, 7, 11)
+    frames = chain.view(4, 4, 7, 11)
+    want0 = torch.cat([xs, hs["categorical"].float(), hs["integer"].float()], dim=2)
+    assert torch.allclose(frames[0], want0, rtol=0, atol=1e-6 * float(want0.abs().max()))
+    assert torch.isfinite(frames).all() and float(frames[3].abs().max()) > 0
+    # padded rows of every frame are zero
+    assert float((frames * (~nm).float().unsqueeze(0)).abs().max()) == 0.0
