@@ -280,3 +280,39 @@ def test_sample_ar_cuda_against_reference(golden_dir, engine, tol):
     print("sample_AR", engine, "logit rel err per step:",
           ["%.2e" % rel(o[1], g["node_predict_%d" % k]) for k, o in enumerate(out)])
     check_ar(out, g, tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["strict", "fp32"])
+def test_cuda_dense_layer_is_equivariant_at_beam_size(engine):
+    """Size-independent property at a size the numpy oracle is too slow for (B=64, N=24: 36 864 edge rows): rotating and
+    translating the coordinates rotates / translates the output coordinates and leaves h and the edge features unchanged
+    (gcl.py:201-209 uses distances and coordinate differences only); permuting the molecules permutes the outputs."""
+    dev = torch.device("cuda", 0)
+    layer, _ = make_layer("equiv", H, True, True, dev)
+    layer.engine = engine
+    B, N = 64, 24
+    g = torch.Generator().manual_seed(8)
+    sizes = torch.randint(1, N + 1, (B,), generator=g)
+    sizes[0] = N
+    nm = (torch.arange(N)[None, :] < sizes[:, None]).float()
+    em = (nm[:, :, None] * nm[:, None, :] * (1 - torch.eye(N))[None]).reshape(-1, 1)
+    nmf = nm.reshape(-1, 1)
+    h = (torch.randn(B * N, H, generator=g) * nmf).to(dev)
+    x = (torch.randn(B * N, 3, generator=g) * nmf).to(dev)
+    e = (torch.randn(B * N * N, H, generator=g) * em).to(dev)
+    sz = sizes.to(torch.int32).to(dev)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    q, t = q.to(dev), torch.randn(1, 3, generator=g).to(dev)
+    h1, x1, e1 = layer.forward_dense(h, x, e, sz, B, N)
+    x_moved = (x @ q + t) * nmf.to(dev)
+    h2, x2, e2 = layer.forward_dense(h, x_moved, e, sz, B, N)
+    scale = float(x1.abs().max())
+    assert float((x2 - (x1 @ q + t) * nmf.to(dev)).abs().max()) < 2e-4 * max(scale, 1.0)
+    assert float((h2 - h1).abs().max()) < 2e-4 * float(h1.abs().max())
+    assert float((e2 - e1).abs().max()) < 2e-4 * float(e1.abs().max())
+    perm = torch.randperm(B, generator=g)
+    pn = (perm[:, None] * N + torch.arange(N)[None, :]).reshape(-1).to(dev)
+    pe = (perm[:, None] * N * N + torch.arange(N * N)[None, :]).reshape(-1).to(dev)
+    h3, x3, e3 = layer.forward_dense(h[pn], x[pn], e[pe], sz[perm.to(dev)], B, N)
+    assert torch.equal(h3, h1[pn]) and torch.equal(x3, x1[pn]) and torch.equal(e3, e1[pe])
