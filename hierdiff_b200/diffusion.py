@@ -262,14 +262,24 @@ class DiffusionQM9(nn.Module):
                           mol_shape, _inject, 1.0)[1:]
 
     def _loss(self, xh, node_mask, edge_mask, context, t0_always, mol_shape, inject, norm_x):
-        if mol_shape is not None and mol_shape != xh.shape[1]:
-            raise NotImplementedError("the pocket-conditioned loss (mol_shape < n_nodes) is not built")
         native.require_cuda(xh)
         B, N, D = xh.shape
         F_ = D - self.n_dims
         dev = xh.device
         L = native.lib()
-        sizes = self._masks_to_sizes(node_mask, edge_mask)
+        xh_fix = None
+        if mol_shape is not None and mol_shape != N:
+            # pocket attached (:556-558, :576-579): the first mol_shape node slots are the ligand the loss is about, the
+            # rest the pocket - appended, un-noised, to every network input and cut from its output again
+            if float(norm_x) != 1.0:
+                raise NotImplementedError("norm_values[0] != 1 together with a pocket is not built")
+            N = int(mol_shape)
+            xh_fix = xh[:, N:].float().contiguous()
+            xh = xh[:, :N]
+            full_mask, full_edge = node_mask, edge_mask
+            sizes = sizes_from_node_mask(node_mask.reshape(B, -1)[:, :N], B, N)
+        else:
+            sizes = self._masks_to_sizes(node_mask, edge_mask)
         xh = xh.float().contiguous()
         lowest = 1 if t0_always else 0
         if inject is not None:
@@ -296,22 +306,29 @@ class DiffusionQM9(nn.Module):
                              "hd_loss_noise_mix")
             return eps, z
 
+        def network(z, time):
+            if xh_fix is None:
+                return self.dynamics.forward_sizes(time, z, sizes, flags=flags, context=context)
+            out = self.phi(torch.cat([z, xh_fix], dim=1), time, full_mask, full_edge, context, mol_shape=N)   # :579-582
+            return out[:, :N].contiguous()
+
         rx, rh = (draws[0], draws[1]) if draws else self._draw(B, N, dev)
         eps_t, z_t = noisy(gamma_t, rx, rh)
-        net_t = self.dynamics.forward_sizes(t, z_t, sizes, flags=flags, context=context)
+        net_t = network(z_t, t)
         eps_0 = z_0 = net_0 = None
         if t0_always:                                                                     # :617-640
             rx0, rh0 = (draws[2], draws[3]) if draws else self._draw(B, N, dev)
             eps_0, z_0 = noisy(gamma_0, rx0, rh0)
-            net_0 = self.dynamics.forward_sizes(zeros, z_0, sizes, flags=flags, context=context)
+            net_0 = network(z_0, zeros)
         cfg = native.HdLossConfig()
         cfg.T, cfg.t0_always = int(self.T), int(bool(t0_always))
         cfg.l2_training = int(self.training and self.loss_type == "l2")
         cfg.int_nf, cfg.cont_nf = (5, 3) if self.node_coarse_type == "prop" else (3, 0)   # :462-467
         cfg.norm_x, cfg.norm_int, cfg.bias_int = float(norm_x), float(self.norm_values[2]), float(self.norm_biases[2])
         nll, loss, error = (torch.empty(B, device=dev) for _ in range(3))
+        t_flat = flat(t_int)
         with torch.cuda.device(dev):
-            native.check(L.hd_loss_terms(cfg, P(xh), P(z_t), P(eps_t), P(net_t), P(z_0), P(eps_0), P(net_0), P(flat(t_int)),
+            native.check(L.hd_loss_terms(cfg, P(xh), P(z_t), P(eps_t), P(net_t), P(z_0), P(eps_0), P(net_0), P(t_flat),
                                          P(gamma_s), P(gamma_t), P(gamma_0), P(gamma_T), P(sizes), B, N, F_, P(nll), P(loss),
                                          P(error), None, st()), "hd_loss_terms")
         self._raise_on_flags(flags)
@@ -322,26 +339,53 @@ class DiffusionQM9(nn.Module):
         """diffusion_qm9.py:675-699: normalise, then one network call (training) or two (eval); returns -log p(x, h) [B]."""
         native.require_cuda(x)
         B, N, _ = x.shape
-        sizes = self._masks_to_sizes(node_mask, edge_mask)
         F_ = h.shape[2]
-        xh = torch.empty(B, N, self.n_dims + F_, device=x.device)
         flags = torch.zeros(1, dtype=torch.int32, device=x.device)
-        with torch.cuda.device(x.device):
-            native.check(native.lib().hd_loss_prepare(
-                native.ptr(x.float().contiguous()), native.ptr(h.float().contiguous()), native.ptr(sizes), B, N, F_,
-                float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]), int(_center),
-                native.ptr(xh), native.ptr(flags), native.stream_ptr()), "hd_loss_prepare")
+
+        def prepare(xb, hb, sizes, center):
+            out = torch.empty(B, xb.shape[1], self.n_dims + F_, device=x.device)
+            xb, hb = xb.float().contiguous(), hb.float().contiguous()   # named: a temporary would be recycled before the launch
+            with torch.cuda.device(x.device):
+                native.check(native.lib().hd_loss_prepare(
+                    native.ptr(xb), native.ptr(hb), native.ptr(sizes), B, xb.shape[1],
+                    F_, float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]), int(center),
+                    native.ptr(out), native.ptr(flags), native.stream_ptr()), "hd_loss_prepare")
+            return out
+
+        if mol_shape is not None and mol_shape != N:
+            # ligand block and pocket block (forward :703-726): the centre of gravity is the LIGAND's
+            # (remove_mean_with_mask(..., fix_size=mol_shape), models/utils.py:43-57) and moves the pocket with it
+            M = int(mol_shape)
+            nm = node_mask.reshape(B, N) != 0
+            lig_sizes, poc_sizes = sizes_from_node_mask(nm[:, :M], B, M), sizes_from_node_mask(nm[:, M:], B, N - M)
+            xl = x[:, :M].float()
+            lig = prepare(xl, h[:, :M], lig_sizes, _center)
+            shift = xl[:, :1] - lig[:, :1, :self.n_dims] * self.norm_values[0]        # the mean that was removed
+            poc = prepare(x[:, M:].float() - shift * nm[:, M:, None].float(), h[:, M:], poc_sizes, False)
+            xh = torch.cat([lig, poc], dim=1)
+        else:
+            xh = prepare(x, h, self._masks_to_sizes(node_mask, edge_mask), _center)
         self._raise_on_flags(flags)
         return self._loss(xh, node_mask, edge_mask, context, not self.training, mol_shape, _inject, self.norm_values[0])[0]
 
     @torch.no_grad()
     def forward(self, batch, _inject=None):
         """diffusion_qm9.py:701-751 (the value ``validation_step`` / ``test_step`` return): {'loss': mean NLL}."""
-        if self.pocket:
-            raise NotImplementedError("the pocket-conditioned loss is not built")
         x, node_mask, edge_mask, h = batch["positions"], batch["atom_mask"], batch["edge_mask"], batch["node_feature"]
         context = batch["context"] if self.cfg.dynamics.context_node_nf > 0 else None
-        return {"loss": self.nll(x, h, node_mask, edge_mask, context=context, _inject=_inject, _center=True).mean(0)}
+        mol_shape = None
+        if self.pocket:   # :703-724: residues as extra node slots, block-diagonal edge mask, embedded residue types
+            B, M, P = x.shape[0], x.shape[1], batch["protein_pos"].shape[1]
+            mol_shape = M
+            x = torch.cat([x, batch["protein_pos"].to(x.dtype)], dim=1)
+            node_mask = torch.cat([node_mask.reshape(B, M, 1), batch["protein_feat_mask"].reshape(B, P, 1)], dim=1)
+            em = torch.zeros(B, M + P, M + P, dtype=edge_mask.dtype, device=edge_mask.device)
+            em[:, :M, :M] = edge_mask.reshape(B, M, M)
+            em[:, M:, M:] = batch["protein_edge_mask"].reshape(B, P, P)
+            edge_mask = em
+            h = torch.cat([h, self.pocket_embed.weight.detach()[batch["protein_feat"].long()].to(h.dtype)], dim=1)
+        return {"loss": self.nll(x, h, node_mask, edge_mask, context=context, mol_shape=mol_shape, _inject=_inject,
+                                 _center=True).mean(0)}
 
     def validation_step(self, batch, batch_idx):
         return self.forward(batch)

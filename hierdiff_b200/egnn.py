@@ -217,10 +217,11 @@ class EGNN(nn.Module):
         """One GCL (egnn_new.py:64-70) of ``e_block_{block}.gcl_{sub}``; returns the new h."""
         native.require_cuda(h)
         h = h.contiguous().float().clone()
+        x, x0 = x.contiguous().float(), x0.contiguous().float()   # named: a temporary's memory would be recycled before the launch
         with torch.cuda.device(h.device):
             native.check(native.lib().hd_gcl_forward(
                 self.hd_config(), native.ptr(self.packed_weights()), block, sub, native.ptr(h),
-                native.ptr(x.contiguous()), native.ptr(x0.contiguous()), native.ptr(sizes), B, N,
+                native.ptr(x), native.ptr(x0), native.ptr(sizes), B, N,
                 native.ptr(self.workspace(B, N, h.device)), self.engine_id(engine), native.stream_ptr()),
                 "hd_gcl_forward")
         return h
@@ -228,11 +229,12 @@ class EGNN(nn.Module):
     def equiv_forward(self, block, h, x, x0, sizes, B, N, engine=None):
         """EquivariantUpdate (egnn_new.py:106-110) of ``e_block_{block}.gcl_equiv``; returns the new x."""
         native.require_cuda(h)
+        h, x, x0 = h.contiguous().float(), x.contiguous().float(), x0.contiguous().float()   # named, as above
         x_out = torch.empty_like(x)
         with torch.cuda.device(h.device):
             native.check(native.lib().hd_equiv_update(
-                self.hd_config(), native.ptr(self.packed_weights()), block, native.ptr(h.contiguous()),
-                native.ptr(x.contiguous()), native.ptr(x0.contiguous()), native.ptr(sizes), B, N,
+                self.hd_config(), native.ptr(self.packed_weights()), block, native.ptr(h),
+                native.ptr(x), native.ptr(x0), native.ptr(sizes), B, N,
                 native.ptr(x_out), native.ptr(self.workspace(B, N, h.device)), self.engine_id(engine),
                 native.stream_ptr()), "hd_equiv_update")
         return x_out

@@ -319,12 +319,12 @@ def case_pocket(name="pocket_l1", n_layers=1, T=6, sizes=(6, 9, 2), P=5, seed=4)
     print(name, "x absmax", float(np.abs(x).max()), "draw shapes", draws[0].shape, draws[1].shape, len(draws))
 
 
-def case_loss(name, n_layers, T, sizes, seed, training, noise_schedule="learned"):
+def case_loss(name, n_layers, T, sizes, seed, training, noise_schedule="learned", P=0):
     """``DiffusionQM9.forward(batch)`` -> ``nll`` -> ``compute_loss`` (diffusion_qm9.py:701-751, :675-699, :530-673)
     of the unmodified reference on CPU: eval mode (t0_always, two network calls) or training mode (one call), no
     gradients.  Recorded: the batch, the timesteps drawn, the raw randn draws in call order and the network outputs, so
     that the CUDA path can be fed the same randomness."""
-    model = make_reference(n_layers, T, noise_schedule=noise_schedule)
+    model = make_reference(n_layers, T, noise_schedule=noise_schedule, pocket=P > 0)
     model.train(training)
     B, N = len(sizes), max(sizes)
     g = torch.Generator().manual_seed(seed)
@@ -334,6 +334,11 @@ def case_loss(name, n_layers, T, sizes, seed, training, noise_schedule="learned"
     # integer-valued categorical part (5 columns), continuous part (3), as the 'prop' coarse features are laid out
     h = torch.cat([torch.randint(0, 4, (B, N, 5), generator=g).float(), torch.randn(B, N, 3, generator=g)], 2) * nm
     batch = {"positions": x.clone(), "atom_mask": node_mask, "edge_mask": edge_mask, "node_feature": h.clone()}
+    if P:   # pocket-conditioned training batch (diffusion_qm9.py:703-724): residues as extra, frozen nodes
+        p_sizes = [P - (i % 3) for i in range(B)]
+        p_mask, p_edge = masks_for(p_sizes, P)
+        batch.update(protein_pos=torch.randn(B, P, 3, generator=g) * 3.0 * p_mask.float(),
+                     protein_feat=torch.randint(0, 21, (B, P), generator=g), protein_feat_mask=p_mask, protein_edge_mask=p_edge)
     draws, nets, ts, gammas = [], [], [], []
     real_randn, real_randint, real_phi = torch.randn, torch.randint, model.phi
     hook = model.gamma.register_forward_hook(lambda m, i, o: gammas.append(o.detach().numpy().copy()))
@@ -360,8 +365,19 @@ def case_loss(name, n_layers, T, sizes, seed, training, noise_schedule="learned"
             out = model.forward(batch)
             # the per-molecule values behind the mean (same draws again)
             torch.manual_seed(seed)
-            xc = x - (x.sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
-            per_mol = model.nll(xc, h, node_mask, edge_mask.view(B, N * N), context=None, mol_shape=None)
+            if P:
+                # the same composition forward() does (:703-726), to reach the per-molecule values
+                pm = batch["protein_feat_mask"]
+                xa = torch.cat([x, batch["protein_pos"]], 1)
+                ma = torch.cat([node_mask, pm], 1)
+                ea = torch.zeros(B, N + P, N + P, dtype=torch.bool)
+                ea[:, :N, :N], ea[:, N:, N:] = edge_mask, batch["protein_edge_mask"]
+                ha = torch.cat([h, model.pocket_embed(batch["protein_feat"])], 1)
+                xa = xa - (x.sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * ma.float()
+                per_mol = model.nll(xa, ha, ma, ea.view(B, (N + P) ** 2), context=None, mol_shape=N)
+            else:
+                xc = x - (x.sum(1, keepdim=True) / nm.sum(1, keepdim=True)) * nm
+                per_mol = model.nll(xc, h, node_mask, edge_mask.view(B, N * N), context=None, mol_shape=None)
     finally:
         torch.randn, torch.randint, model.phi = real_randn, real_randint, real_phi
         hook.remove()
@@ -375,6 +391,9 @@ def case_loss(name, n_layers, T, sizes, seed, training, noise_schedule="learned"
         rec["randn_%d" % i] = draws[i]
     for i in range(len(nets) // 2):
         rec["net_%d" % i] = nets[i]
+    if P:
+        rec.update(protein_pos=batch["protein_pos"].numpy(), protein_feat=batch["protein_feat"].numpy(),
+                   protein_sizes=np.array(p_sizes, np.int32))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
     print(name, "loss", float(out["loss"]), "t", ts[0].ravel().tolist(), "draws", [d.shape for d in draws[:k]])
 
@@ -409,6 +428,7 @@ def case_nodes_dist():
 if __name__ == "__main__" and "--loss-only" in sys.argv:
     case_loss("loss_eval_l2", 2, 1000, [7, 4, 9, 1], 11, training=False)
     case_loss("loss_train_l1", 1, 3, [6, 9, 2, 5, 8, 3], 13, training=True)      # T = 3: two molecules draw t = 0
+    case_loss("loss_pocket_l1", 1, 1000, [6, 9, 2], 14, training=False, P=5)
     sys.exit(0)
 
 if __name__ == "__main__":
