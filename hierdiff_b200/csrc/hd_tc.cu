@@ -72,7 +72,10 @@ constexpr int MAX_MOL = 4096;         // molecules per launch
 constexpr int NPW = 8;                // producer warps
 constexpr int NEW = 8;                // epilogue warps
 constexpr int PROD_THREADS = 32 * NPW, EPI_THREADS = 32 * NEW;
-constexpr int NTHREADS = PROD_THREADS + EPI_THREADS + 64;   // + MMA/alloc warp + metadata warp
+#ifndef HD_EXP_IDLE_WARPS
+#define HD_EXP_IDLE_WARPS 0   // timing experiment only: extra idle warps (what a lower register cap alone costs)
+#endif
+constexpr int NTHREADS = PROD_THREADS + EPI_THREADS + 64 + 32 * HD_EXP_IDLE_WARPS;   // + MMA/alloc warp + metadata warp
 #ifdef HD_EXP_NO_FILL_HELP
 constexpr bool FILL_HELP = false;
 #else
@@ -888,7 +891,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_tc_k(const Params p) {
         if (FILL_HELP && t == 0) ptx::mbar_arrive(bar_meta0);
       }
     }
-  } else {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       ptx::mbar_wait(bar_wl, 0);
