@@ -113,12 +113,18 @@ static Work work(const hd_egcl_config& c, int64_t n_nodes, int64_t E) {
 // i, j < n_b and i != j (the prefix node masks / off-diagonal edge masks of the sampler's batches).  Explicit list:
 // row[e], col[e], multiplier emask[e] (null: 1).
 struct EdgeSrc {
-  const int32_t *row, *col;
+  const int32_t *row, *col;       // explicit list, 32-bit indices ...
   const float* emask;
   const int32_t* sizes;
   int N;
+  const int64_t *row64, *col64;   // ... or 64-bit ones (torch's edge_index as it is)
 };
 __device__ __forceinline__ float edge_get(const EdgeSrc& s, int64_t e, int& row, int& col) {
+  if (s.row64) {
+    row = (int)s.row64[e];
+    col = (int)s.col64[e];
+    return s.emask ? s.emask[e] : 1.f;
+  }
   if (s.row) {
     row = s.row[e];
     col = s.col[e];
@@ -291,8 +297,10 @@ __global__ void mes1_k(const float* __restrict__ ab, const float* __restrict__ p
     v = fmaf(r, w0[(int64_t)k * ldw + col_r], v);
     if (pe) {
       v += pe[e * Hh + k];
-    } else {
+    } else if (edge_attr) {
       for (int d = 0; d < De; ++d) v = fmaf(edge_attr[e * De + d], w0[(int64_t)k * ldw + col_r + 1 + d], v);
+    } else {
+      v = fmaf(r, w0[(int64_t)k * ldw + col_r + 1], v);   // edge_attr == NULL, De == 1: the edge feature IS the squared distance
     }
     m1[e * Hh + k] = silu_acc(v);
   }
@@ -511,7 +519,7 @@ static int egcl_dense_tc(const hd_egcl_config* cfg, const float* w, const char* 
   if ((rc = linear_tc_rows(st, E, WF(W.m1), Hh, Hh, nullptr, 0, 0, P + K.w2_hi, P + K.w2_lo, Hh, w + o.mes2_b, WF(W.m), Hh, 1,
                            nullptr, nullptr, nullptr, nullptr, sizes, N, strict)))
     return rc;
-  const egcl::EdgeSrc es{nullptr, nullptr, nullptr, sizes, N};
+  const egcl::EdgeSrc es{nullptr, nullptr, nullptr, sizes, N, nullptr, nullptr};
   egcl::att_k<<<(E + 7) / 8, 256, 0, st>>>(WF(W.m), cfg->attention ? w + o.att_w : nullptr,
                                        cfg->attention ? w + o.att_b : nullptr, cfg->attention, es, Hh, E);
   HD_CHECK_LAUNCH();
@@ -540,10 +548,10 @@ static int egcl_dense_tc(const hd_egcl_config* cfg, const float* w, const char* 
 }
 
 HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const void* packed, const float* h,
-                               const float* x, const float* edge_attr, const int32_t* row, const int32_t* col,
-                               const float* edge_mask, const float* node_mask, const int32_t* sizes, int32_t B, int32_t N,
-                               int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out, float* edge_out,
-                               void* workspace, int32_t engine, hd_stream_t stream) {
+                               const float* x, const float* edge_attr, const void* row, const void* col,
+                               int32_t index_bits, const float* edge_mask, const float* node_mask, const int32_t* sizes,
+                               int32_t B, int32_t N, int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out,
+                               float* edge_out, void* workspace, int32_t engine, hd_stream_t stream) {
   if (!cfg || !w || !h || !x || !h_out || !x_out || !workspace) {
     set_error("null argument");
     return HD_E_INVALID;
@@ -560,7 +568,14 @@ HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const 
     set_error("explicit edge list needs row, col, n_nodes >= 1, n_edges >= 0");
     return HD_E_INVALID;
   }
-  if (n_edges > 0 && (!edge_attr || (cfg->edge_update && !edge_out))) {
+  if (index_bits != 32 && index_bits != 64) {
+    set_error("index_bits must be 32 or 64");
+    return HD_E_INVALID;
+  }
+  // edge_attr == NULL with one edge feature and no edge update: the feature is |x_row - x_col|^2, computed here
+  // (what edge_denoise.py:345-347 / :396-398 pass to gcl_edge / gcl_denoise)
+  const bool radial_attr = !edge_attr && cfg->edges_in_d == 1 && !cfg->edge_update;
+  if (n_edges > 0 && ((!edge_attr && !radial_attr) || (cfg->edge_update && !edge_out))) {
     set_error("null edge_attr / edge_out");
     return HD_E_INVALID;
   }
@@ -591,7 +606,10 @@ HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const 
   auto WF = [&](int64_t off) { return reinterpret_cast<float*>(ws + off); };
   const int Hh = cfg->hidden_nf, De = cfg->edges_in_d;
   const int BN = (int)n_nodes, E = (int)n_edges;
-  const egcl::EdgeSrc es{row, col, edge_mask, dense ? sizes : nullptr, N};
+  const bool wide = !dense && index_bits == 64;
+  const egcl::EdgeSrc es{wide ? nullptr : static_cast<const int32_t*>(row), wide ? nullptr : static_cast<const int32_t*>(col),
+                         edge_mask, dense ? sizes : nullptr, N, wide ? static_cast<const int64_t*>(row) : nullptr,
+                         wide ? static_cast<const int64_t*>(col) : nullptr};
   const egcl::NodeSrc ns{node_mask, dense ? sizes : nullptr, N};
   const bool has_emask = dense || edge_mask != nullptr;
   const bool has_nmask = dense || node_mask != nullptr;

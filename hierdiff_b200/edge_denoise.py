@@ -112,8 +112,7 @@ class Edge_denoise(nn.Module):
         for pairs in depths:
             row, col = flat[0, at:at + len(pairs)], flat[1, at:at + len(pairs)]
             at += len(pairs)
-            radial = ((x[row] - x[col]) ** 2).sum(1, keepdim=True)
-            h, x = layer(h, [row, col], x, edge_attr=radial, node_mask=node_mask)
+            h, x = layer.forward_radial(h, [row, col], x, node_mask=node_mask)   # edge_attr = |x_row - x_col|^2
         return h, x
 
     @staticmethod

@@ -21,7 +21,7 @@ FLAG_NAN = 1
 FLAG_COG = 2
 FLAG_MASK = 4
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class HdConfig(ctypes.Structure):
@@ -91,7 +91,7 @@ SIGNATURES = {
     "hd_egcl_workspace_bytes": (_L, [_ECFG, _L, _L]),
     "hd_egcl_packed_bytes": (_L, [_ECFG]),
     "hd_egcl_pack_weights": (_I, [_ECFG, _P, _P, _P]),
-    "hd_egcl_forward": (_I, [_ECFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P]),
+    "hd_egcl_forward": (_I, [_ECFG, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P]),
 }
 
 _lib = None

@@ -54,7 +54,6 @@ class E_GCL(nn.Module):
             self.att_mlp = nn.Sequential(nn.Linear(hidden_nf, 1), nn.Sigmoid())
         self.engine = "strict"  # dense list with hidden_nf = edges_in_d = 256: "strict" | "fast" (tcgen05) | "fp32"
         self._flat = None      # (version key, flat fp32 parameter buffer on the device, packed tensor-core image or None)
-        self._edges = None     # (row64, col64, row32, col32): int32 copies of the last edge_index (held by identity)
         self._ws = None
 
     # ------------------------------------------------------------------ native plumbing
@@ -82,12 +81,13 @@ class E_GCL(nn.Module):
             self._flat = (key, flat, packed)
         return self._flat[1], self._flat[2]
 
-    def _edge_i32(self, edge_index):
+    @staticmethod
+    def _indices(edge_index):
+        """(row, col) as the library takes them: int64 (torch's edge_index) or int32, contiguous."""
         row, col = edge_index
-        hit = self._edges
-        if hit is None or hit[0] is not row or hit[1] is not col:
-            self._edges = hit = (row, col, row.to(torch.int32).contiguous(), col.to(torch.int32).contiguous())
-        return hit[2], hit[3]
+        if row.dtype not in (torch.int32, torch.int64) or col.dtype != row.dtype:
+            row, col = row.long(), col.long()
+        return row.contiguous(), col.contiguous()
 
     def _workspace(self, cfg, n_nodes, n_edges, device):
         need = native.lib().hd_egcl_workspace_bytes(cfg, n_nodes, n_edges)
@@ -104,8 +104,18 @@ class E_GCL(nn.Module):
         if node_attr is not None or edge_attr is None:
             raise NotImplementedError("node_attr is unused by the stage-2 decoder; edge_attr is required")
         native.require_cuda(h)
-        row, col = self._edge_i32(edge_index)
+        row, col = self._indices(edge_index)
         return self._run(h, coord, edge_attr, row, col, edge_mask, node_mask, None, 0, 0)
+
+    @torch.no_grad()
+    def forward_radial(self, h, edge_index, coord, node_mask=None, edge_mask=None):
+        """``forward`` with ``edge_attr = |x_row - x_col|^2`` (edge_denoise.py:345-347, :396-398: what ``gcl_edge`` /
+        ``gcl_denoise`` are given), the distance computed inside the kernel instead of by four torch launches."""
+        if self.edges_in_d != 1 or self.edge_update:
+            raise NotImplementedError("forward_radial is for the one-feature layers without edge update")
+        native.require_cuda(h)
+        row, col = self._indices(edge_index)
+        return self._run(h, coord, None, row, col, edge_mask, node_mask, None, 0, 0)
 
     @torch.no_grad()
     def forward_dense(self, h, coord, edge_attr, sizes, B, N):
@@ -119,7 +129,8 @@ class E_GCL(nn.Module):
         n_nodes = h.shape[0]
         n_edges = n_nodes * N if row is None else row.numel()
         f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
-        h, coord, edge_attr = f32(h), f32(coord), f32(edge_attr).reshape(n_edges, self.edges_in_d)
+        h, coord = f32(h), f32(coord)
+        edge_attr = None if edge_attr is None else f32(edge_attr).reshape(n_edges, self.edges_in_d)
         if h.shape[1] != self.hidden_nf or coord.shape != (n_nodes, 3):
             raise ValueError("h / coord / edge_attr shapes do not match the layer")
         em = None if edge_mask is None else f32(edge_mask).reshape(-1)
@@ -134,7 +145,8 @@ class E_GCL(nn.Module):
         e_out = torch.empty(n_edges, self.hidden_nf, device=dev) if self.edge_update else None
         P = native.ptr
         with torch.cuda.device(dev):
-            native.check(native.lib().hd_egcl_forward(cfg, P(w), P(packed), P(h), P(coord), P(edge_attr), P(row), P(col),
+            bits = 32 if (row is not None and row.dtype == torch.int32) else 64
+            native.check(native.lib().hd_egcl_forward(cfg, P(w), P(packed), P(h), P(coord), P(edge_attr), P(row), P(col), bits,
                                                       P(em), P(nm), P(sizes), B, N, n_nodes, n_edges, P(h_out), P(x_out),
                                                       P(e_out), P(ws), engine, native.stream_ptr()), "hd_egcl_forward")
         return (h_out, x_out, e_out) if self.edge_update else (h_out, x_out)

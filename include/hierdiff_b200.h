@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HD_ABI_VERSION 9
+#define HD_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define HD_API __attribute__((visibility("default")))
@@ -218,11 +218,14 @@ HD_API int32_t hd_edge_kernel_only(const hd_config* cfg, const void* packed, int
  *   coord_mlp.0.{weight, bias}, coord_mlp.2.weight [1,H], [att_mlp.0.{weight [1,H], bias [1]} if attention].
  * Edges: row == NULL selects the DENSE list of edge_denoise.py:506-524 (edge e = (b, i, j), row = b*N+i, col = b*N+j,
  * n_nodes = B*N, n_edges = B*N*N) with node_mask / edge_mask derived from `sizes` (prefix node masks, off-diagonal
- * edge masks; edge_mask / node_mask arguments ignored); otherwise row/col [n_edges] index the n_nodes rows of h and
+ * edge masks; edge_mask / node_mask arguments ignored); otherwise row/col [n_edges] index the n_nodes rows of h
+ * (int32 or int64 elements: index_bits = 32 / 64, the latter being torch's edge_index as it is),
  * edge_mask [n_edges] / node_mask [n_nodes] are optional float multipliers (NULL = the reference's None) and
  * sizes (NULL) / B / N are ignored; an empty list (n_edges = 0, all edge pointers NULL) is valid.  Messages aggregate over `col` (gcl.py:121).  h, h_out [n_nodes, H]; x, x_out
  * [n_nodes, 3] (x_out must not alias x); edge_attr [n_edges, De]; edge_out [n_edges, H] when edge_update (may alias
- * nothing).  The dense reduction is deterministic; the explicit list is reduced with fp32 atomics. */
+ * nothing).  edge_attr == NULL with edges_in_d = 1 and no edge update: the edge feature is |x_row - x_col|^2, computed in the
+ * kernel (what edge_denoise.py:345-347, :396-398 pass to gcl_edge / gcl_denoise).  The dense reduction is deterministic;
+ * the explicit list is reduced with fp32 atomics. */
 typedef struct {
   int32_t hidden_nf;    /* H: input_nf = output_nf = hidden_nf */
   int32_t edges_in_d;   /* De */
@@ -244,10 +247,10 @@ HD_API int64_t hd_egcl_workspace_bytes(const hd_egcl_config* cfg, int64_t n_node
 HD_API int64_t hd_egcl_packed_bytes(const hd_egcl_config* cfg);
 HD_API int32_t hd_egcl_pack_weights(const hd_egcl_config* cfg, const float* w, void* packed, hd_stream_t stream);
 HD_API int32_t hd_egcl_forward(const hd_egcl_config* cfg, const float* w, const void* packed, const float* h,
-                               const float* x, const float* edge_attr, const int32_t* row, const int32_t* col,
-                               const float* edge_mask, const float* node_mask, const int32_t* sizes, int32_t B, int32_t N,
-                               int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out, float* edge_out,
-                               void* workspace, int32_t engine, hd_stream_t stream);
+                               const float* x, const float* edge_attr, const void* row, const void* col,
+                               int32_t index_bits, const float* edge_mask, const float* node_mask, const int32_t* sizes,
+                               int32_t B, int32_t N, int64_t n_nodes, int64_t n_edges, float* h_out, float* x_out,
+                               float* edge_out, void* workspace, int32_t engine, hd_stream_t stream);
 
 /* ---- forward value of the diffusion loss / NLL: the glue of DiffusionQM9.forward -> nll ->
  * compute_loss (train_module/diffusion_qm9.py:701-751, :675-699, :530-673) around the network calls (hd_dynamics_forward

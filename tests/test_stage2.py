@@ -242,6 +242,9 @@ def test_sample_ar_host_logic_against_reference(golden_dir, monkeypatch):
             row, col = row.numpy(), col.numpy()
             nm = None if node_mask is None else node_mask.numpy().reshape(-1, 1)
             em = None if edge_mask is None else edge_mask.numpy().reshape(-1, 1)
+        if edge_attr is None:     # forward_radial: the edge feature is the squared distance (edge_denoise.py:345-347)
+            d = coord.numpy()[row] - coord.numpy()[col]
+            edge_attr = torch.from_numpy((d * d).sum(1, keepdims=True).astype(np.float32))
         o = EO.egcl_forward(w, h.numpy(), coord.numpy(), edge_attr.numpy().reshape(len(row), -1), nm, em, row, col,
                             self.attention, self.tanh, float(self.coords_range), self.edge_update)
         return tuple(torch.from_numpy(a) for a in o if a is not None)
