@@ -246,6 +246,40 @@ def test_argument_checks_of_the_ragged_entry_point_need_no_gpu():
     assert call(2, 129, 0) == -1 and b"N" in L.hd_last_error()
 
 
+def test_stage2_and_loss_entry_points_validate_before_touching_the_device():
+    """hd_egcl_* / hd_linear_forward / hd_loss_*: sizes come from the configuration alone, bad arguments return
+    HD_E_INVALID / HD_E_UNSUPPORTED with a message - none of this needs a GPU."""
+    from hierdiff_b200 import native
+    L = native.lib()
+    full = native.HdEgclConfig(256, 256, 1, 1, 30.0, 1)     # gcl_full_*: hidden edge features, attention, edge update
+    plain = native.HdEgclConfig(256, 1, 0, 1, 30.0, 0)      # gcl_edge / gcl_denoise
+    H = 256
+    n_full = (H * (2 * H + 1 + H) + H) + (H * H + H) + (H * (H + 1 + H) + H) + (H * H + H) + (H * 2 * H + H) + (H * H + H) \
+        + (H * H + H) + H + (H + 1)
+    assert L.hd_egcl_weight_count(ctypes.byref(full)) == n_full
+    assert L.hd_egcl_packed_bytes(ctypes.byref(full)) > 0 and L.hd_egcl_packed_bytes(ctypes.byref(plain)) == 0
+    assert L.hd_egcl_workspace_bytes(ctypes.byref(full), 10, 100) > 100 * H * 4 * 4
+    one = ctypes.c_void_p(16)   # never dereferenced
+
+    def egcl(cfg, row, col, bits, sizes, B, N, n_nodes, n_edges, edge_attr=one, packed=None, engine=native.ENGINE_FP32):
+        return L.hd_egcl_forward(ctypes.byref(cfg), one, packed, one, one, edge_attr, row, col, bits, None, None, sizes, B, N,
+                                 n_nodes, n_edges, one, one, one, one, engine, None)
+
+    assert egcl(full, None, one, 32, one, 2, 5, 0, 0) == -1 and b"dense" in L.hd_last_error()       # dense list with a col
+    assert egcl(full, one, None, 32, None, 0, 0, 10, 4) == -1 and b"explicit" in L.hd_last_error()   # list without col
+    assert egcl(full, one, one, 16, None, 0, 0, 10, 4) == -1 and b"index_bits" in L.hd_last_error()
+    assert egcl(full, one, one, 64, None, 0, 0, 10, 4, edge_attr=None) == -1                          # hidden features need edge_attr
+    assert egcl(plain, None, None, 32, one, 2, 5, 0, 0, engine=native.ENGINE_TC_STRICT) == -3        # no tensor-core path: De = 1
+    assert b"tensor-core" in L.hd_last_error()
+    assert L.hd_linear_forward(one, 4, 0, one, None, 8, 0, one, None) == -1
+    lc = native.HdLossConfig(1000, 1, 0, 5, 3, 1.0, 1.0, 0.0)
+    assert L.hd_loss_terms(ctypes.byref(lc), *([one] * 3), one, None, None, None, *([one] * 6), 2, 5, 8, one, one, one, None,
+                           None) == -1                                                            # t0_always without z_0
+    lc.int_nf = 9                                                                                  # more columns than F
+    assert L.hd_loss_terms(ctypes.byref(lc), *([one] * 13), 2, 5, 8, one, one, one, None, None) == -1
+    assert L.hd_loss_prepare(one, one, one, 0, 5, 8, 1.0, 1.0, 0.0, 1, one, None, None) == -1
+
+
 def test_ragged_rows_rule():
     """SamplingLoop.ragged_rows_pay: the hint is set only for batches beyond one wave of node-GEMM CTAs with at least
     a quarter of padding."""
