@@ -125,6 +125,31 @@ def test_seeded_sample_matches_reference_t1000(tmp_path):
     assert ex < 1e-4 and eh < 1e-4, (ex, eh)
 
 
+@pytest.mark.parametrize("name,L,sizes", [
+    ("configs1_full", 4, [40] * 64),
+    ("configs4_full", 9, None),      # GEOM-drugs config: 9 blocks, sizes drawn from the GEOM histogram as the reference does
+])
+def test_seeded_sample_matches_reference_at_full_baseline_configs(tmp_path, name, L, sizes):
+    """BASELINE.json configs[1] (B=64, N=40, L=4) and configs[4] (GEOM-drugs: L=9, B=64, GEOM sizes) with the full
+    T=1000 chain: the product ``sample_padded`` against the unmodified reference's ``sample`` on the same GPU under the
+    same seed (the reference takes 20-30 s here).  Asserted at the 1e-4 of SURVEY.md 8d, measured values recorded."""
+    T, seed, B = 1000, 0, 64
+    ref = R.make_reference(L, T).to(dev())
+    if sizes is None:
+        torch.manual_seed(123)
+        sizes = [int(v) for v in ref.nodes_dist.sample(B)]
+    x_ref, h_ref = R.sample_padded(ref, sizes, dev(), seed)
+    del ref
+    model = make_model(tmp_path, L, timesteps=T, device=dev(), engine="strict")
+    torch.manual_seed(seed)
+    x, h = model.sample_padded(sizes, dev())
+    ex, eh = rel(x.numpy(), x_ref), rel(h.numpy(), h_ref)
+    record(name + "_t1000_strict", {"x": ex, "h": eh, "max_abs_x_ref": float(np.abs(x_ref).max()), "n_max": max(sizes),
+                                    "n_mean": float(np.mean(sizes))})
+    assert np.isfinite(x.numpy()).all()
+    assert ex < 1e-4 and eh < 1e-4, (ex, eh)
+
+
 def test_seeded_conditioned_sample_matches_reference(tmp_path):
     """sample(context=c) (diffusion_qm9.py:351-352): conditioned chain vs the reference on the same device."""
     sizes, L, T, seed, c = [6, 9, 2], 1, 6, 3, 0.7
